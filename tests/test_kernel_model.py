@@ -1,0 +1,93 @@
+"""The kernel's algorithm (tests/kernel_model.py) against the oracle's closed form and autograd."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sot_oracle as O
+from sot_b200 import synthetic as S
+from tests import kernel_model as KM
+
+
+def _frames(n_fft, n_frames, seed):
+    x, y = S.sot_batch(max(1, -(-n_frames // 16)), n_fft, seed=seed)
+    F = x.shape[-1]
+    return x.reshape(-1, F)[:n_frames].numpy(), y.reshape(-1, F)[:n_frames].numpy()
+
+
+@pytest.mark.parametrize("n_fft,T,L", [(512, 32, 17), (512, 7, 80), (2048, 128, 17)])
+@pytest.mark.parametrize("cut", [True, False])
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_walk_matches_closed_form_bit_exact(n_fft, T, L, cut, p):
+    x, y = _frames(n_fft, 6 if n_fft == 2048 else 16, seed=123)
+    pos = S.linear_positions(n_fft).numpy()
+    for r in range(x.shape[0]):
+        *_, cu, cv = KM.normalise(x[r], y[r], True, cut)
+        loss, g_cu, g_cv = KM.walk_frame(cu, cv, pos, pos, p, cut, T, L)
+        ref_loss, r_cu, r_cv, _, _ = O.closed_form_from_cdfs(cu, cv, pos, pos, p, cut)
+        assert np.array_equal(g_cu, r_cu), f"frame {r}: dL/dcu"
+        assert np.array_equal(g_cv, r_cv), f"frame {r}: dL/dcv"
+        assert abs(loss - float(ref_loss)) <= 2e-6 * abs(float(ref_loss)) + 1e-12
+
+
+def test_walk_ties_and_long_plateaus():
+    # heavy exact ties: many zero weights, identical spectra, and a plateau spanning many threads
+    rng = np.random.default_rng(0)
+    n = 200
+    pos = np.linspace(0, 1, n).astype(np.float32)
+    for trial in range(30):
+        wu = rng.random(n).astype(np.float32) * (rng.random(n) < 0.15)
+        wv = rng.random(n).astype(np.float32) * (rng.random(n) < 0.15)
+        if trial % 3 == 0:
+            wv = wu.copy()
+        if trial % 5 == 0:
+            wu[60:] = 0
+        wu[0] += 1e-3
+        wv[0] += 1e-3
+        cu = np.cumsum((wu / wu.sum()).astype(np.float64)).astype(np.float32)
+        cv = np.cumsum((wv / wu.sum()).astype(np.float64)).astype(np.float32)
+        for T, L in ((32, 13), (128, 4), (400, 1)):
+            for limit in (False, True):
+                loss, g_cu, g_cv = KM.walk_frame(cu, cv, pos, pos, 2, limit, T, L)
+                ref_loss, r_cu, r_cv, _, _ = O.closed_form_from_cdfs(cu, cv, pos, pos, 2, limit)
+                assert np.array_equal(g_cu, r_cu) and np.array_equal(g_cv, r_cv)
+                assert abs(loss - float(ref_loss)) <= 2e-6 * abs(float(ref_loss)) + 1e-12
+
+
+def test_unequal_supports():
+    rng = np.random.default_rng(1)
+    n, m = 37, 90
+    pu = np.sort(rng.random(n)).astype(np.float32)
+    pv = np.sort(rng.random(m)).astype(np.float32)
+    cu = np.cumsum(rng.random(n) / n).astype(np.float32)
+    cv = np.cumsum(rng.random(m) / m * 1.3).astype(np.float32)
+    for limit in (False, True):
+        loss, g_cu, g_cv = KM.walk_frame(cu, cv, pu, pv, 2, limit, 32, 4)
+        ref_loss, r_cu, r_cv, _, _ = O.closed_form_from_cdfs(cu, cv, pu, pv, 2, limit)
+        assert np.array_equal(g_cu, r_cu) and np.array_equal(g_cv, r_cv)
+        assert abs(loss - float(ref_loss)) <= 2e-6 * abs(float(ref_loss))
+
+
+@pytest.mark.parametrize("cut", [True, False])
+def test_end_to_end_model_vs_stable_autograd(cut):
+    """From magnitudes: the model's fp64-accumulated masses/CDFs make it (nearly always) land on
+    the same fp32 CDFs as the CPU reference, so loss and gradients agree with the stable-sort
+    autograd oracle to rounding."""
+    x, y = _frames(512, 32, seed=456)
+    pos = S.linear_positions(512)
+    rows, gx, gy = O.sot_loss_and_grads(torch.from_numpy(x), torch.from_numpy(y), pos, pos,
+                                        upstream=torch.ones(x.shape[0]), p=2, square=True,
+                                        cut_scale=cut, limit=cut, stable=True)
+    uq, vq, qs, cu_ref, cv_ref, _, _ = O.sot_quantiles(torch.from_numpy(x), torch.from_numpy(y),
+                                                     pos, pos, square=True, cut_scale=cut,
+                                                     stable=True)
+    same_cdf = 0
+    for r in range(x.shape[0]):
+        loss, mgx, mgy, cu, cv, _, _ = KM.frame_loss_and_grads(x[r], y[r], pos.numpy(), pos.numpy(),
+                                                              2, True, cut, cut, 32, 17)
+        if np.array_equal(cu, cu_ref[r].numpy()) and np.array_equal(cv, cv_ref[r].numpy()):
+            same_cdf += 1
+            assert abs(loss - rows[r].item()) <= 2e-6 * abs(rows[r].item())
+            ngx, ngy = gx[r].numpy(), gy[r].numpy()
+            assert np.linalg.norm(mgx - ngx) <= 2e-5 * np.linalg.norm(ngx)
+            assert np.linalg.norm(mgy - ngy) <= 2e-5 * np.linalg.norm(ngy)
+    assert same_cdf >= x.shape[0] // 4, f"only {same_cdf} frames reproduced the reference CDFs"
