@@ -1,0 +1,258 @@
+"""ctypes binding of `libsot_b200.so` (C ABI declared in include/sot_b200.h).
+
+This is the only way the Python layer reaches the kernels.  There is no fallback: if the library
+cannot be loaded (or built) every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+SOT_SQUARE, SOT_CUT_SCALE, SOT_LIMIT, SOT_RAW_WEIGHTS = 1, 2, 4, 8
+ABI_VERSION = 1
+
+_c_float_p = ctypes.c_void_p  # device pointers travel as integers
+
+
+class SotProblem(ctypes.Structure):
+    """`struct sot_problem` of include/sot_b200.h."""
+    _fields_ = [
+        ("n_frames", ctypes.c_int64),
+        ("n_u", ctypes.c_int32),
+        ("n_v", ctypes.c_int32),
+        ("u", ctypes.c_void_p),
+        ("v", ctypes.c_void_p),
+        ("pos_u", ctypes.c_void_p),
+        ("pos_v", ctypes.c_void_p),
+        ("pos_u_stride", ctypes.c_int64),
+        ("pos_v_stride", ctypes.c_int64),
+        ("p", ctypes.c_float),
+        ("flags", ctypes.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); kept in one place so tests can check the exported symbol table
+_P = ctypes.POINTER(SotProblem)
+_V = ctypes.c_void_p
+SIGNATURES = {
+    "sot_forward_device": (ctypes.c_int, [_P, _V, _V]),
+    "sot_forward_backward_device": (ctypes.c_int, [_P, _V, _V, _V, _V, _V]),
+    "sot_scale_rows_device": (ctypes.c_int, [_V, _V, _V, ctypes.c_int64, ctypes.c_int32, _V]),
+    "sot_quantiles_device": (ctypes.c_int, [_P, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "sot_quantile_lookup_device": (ctypes.c_int, [_V, _V, _V, _V, ctypes.c_int64, ctypes.c_int32,
+                                                  ctypes.c_int32, _V]),
+    "sot_plan_from_cdf_device": (ctypes.c_int, [_P, _V, _V, _V, _V, _V, _V]),
+    "sot_loss_from_cdf_device": (ctypes.c_int, [_P, _V, _V, _V, _V]),
+    "sot_loss_grad_host": (ctypes.c_int, [_P, _V, _V, _V, _V, ctypes.c_int32]),
+    "sot_abi_version": (ctypes.c_int, []),
+    "sot_last_error": (ctypes.c_char_p, []),
+    "sot_max_bins": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32]),
+    "sot_set_tuning": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32]),
+    "sot_launch_count": (ctypes.c_int64, []),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class SotError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_needed: bool = True):
+    """Load (building first if the in-tree library is missing or stale) and return the CDLL."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if build_if_needed and _build.is_stale():
+            _build.build()
+        if not os.path.exists(_build.LIB_PATH):
+            raise SotError(f"{_build.LIB_PATH} is missing: build it with `python -m sot_b200.build` "
+                           "(this package has no CPU or eager fallback)")
+        lib = ctypes.CDLL(_build.LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+            fn.restype, fn.argtypes = res, args
+        if lib.sot_abi_version() != ABI_VERSION:
+            raise SotError("libsot_b200.so ABI version mismatch: rebuild with `python -m sot_b200.build --force`")
+        _lib = lib
+        return lib
+
+
+def _check(rc: int):
+    if rc == 0:
+        return
+    msg = load().sot_last_error().decode("utf-8", "replace")
+    if rc == -3:
+        raise AssertionError(msg)  # p < 1: the reference asserts (losses.py:271)
+    if rc < 0:
+        raise ValueError(f"sot_b200: {msg}")
+    raise SotError(f"sot_b200 CUDA error {rc}: {msg}")
+
+
+def _dev_tensor(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise SotError(f"sot_b200: `{name}` lives on {t.device}; the SOT kernels are CUDA only "
+                       "(no CPU fallback exists by design)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"sot_b200: `{name}` must be float32, got {t.dtype}")
+    return t
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def make_problem(u, v, pos_u, pos_v, p: float, flags: int) -> SotProblem:
+    """u: (N, n), v: (N, m) contiguous CUDA float32; pos_*: (n,) shared or (N, n) per frame."""
+    _dev_tensor(u, "x"), _dev_tensor(v, "y"), _dev_tensor(pos_u, "x_pos"), _dev_tensor(pos_v, "y_pos")
+    if u.ndim != 2 or v.ndim != 2 or u.shape[0] != v.shape[0]:
+        raise ValueError(f"sot_b200: expected (N, n) and (N, m) rows, got {tuple(u.shape)} and {tuple(v.shape)}")
+    if not (u.is_contiguous() and v.is_contiguous() and pos_u.is_contiguous() and pos_v.is_contiguous()):
+        raise ValueError("sot_b200: tensors must be contiguous")
+    if len({u.device, v.device, pos_u.device, pos_v.device}) != 1:
+        raise ValueError("sot_b200: all tensors must be on the same CUDA device")
+    N, n = u.shape
+    m = v.shape[1]
+    strides = []
+    for pos, width, name in ((pos_u, n, "x_pos"), (pos_v, m, "y_pos")):
+        if pos.ndim == 1 and pos.shape[0] == width:
+            strides.append(0)
+        elif pos.ndim == 2 and tuple(pos.shape) == (N, width):
+            strides.append(width)
+        else:
+            raise ValueError(f"sot_b200: `{name}` has shape {tuple(pos.shape)}, expected ({width},) or ({N}, {width})")
+    return SotProblem(N, n, m, u.data_ptr(), v.data_ptr(), pos_u.data_ptr(), pos_v.data_ptr(),
+                      strides[0], strides[1], float(p), int(flags))
+
+
+def forward(u, v, pos_u, pos_v, p, flags) -> torch.Tensor:
+    lib = load()
+    prob = make_problem(u, v, pos_u, pos_v, p, flags)
+    loss = torch.empty(u.shape[0], dtype=torch.float32, device=u.device)
+    with torch.cuda.device(u.device):
+        _check(lib.sot_forward_device(ctypes.byref(prob), _ptr(loss), _stream(u.device)))
+    return loss
+
+
+def forward_backward(u, v, pos_u, pos_v, p, flags, upstream=None, want_loss=True, want_gu=True, want_gv=True):
+    lib = load()
+    prob = make_problem(u, v, pos_u, pos_v, p, flags)
+    if upstream is not None:
+        _dev_tensor(upstream, "upstream")
+        if upstream.shape != (u.shape[0],) or not upstream.is_contiguous():
+            raise ValueError("sot_b200: upstream gradient must be a contiguous (N,) tensor")
+    loss = torch.empty(u.shape[0], dtype=torch.float32, device=u.device) if want_loss else None
+    gu = torch.empty_like(u) if want_gu else None
+    gv = torch.empty_like(v) if want_gv else None
+    with torch.cuda.device(u.device):
+        _check(lib.sot_forward_backward_device(ctypes.byref(prob), _ptr(upstream), _ptr(loss), _ptr(gu), _ptr(gv),
+                                               _stream(u.device)))
+    return loss, gu, gv
+
+
+def scale_rows(unit, scale) -> torch.Tensor:
+    lib = load()
+    _dev_tensor(unit, "unit"), _dev_tensor(scale, "scale")
+    out = torch.empty_like(unit)
+    with torch.cuda.device(unit.device):
+        _check(lib.sot_scale_rows_device(_ptr(unit), _ptr(scale), _ptr(out), unit.shape[0], unit.shape[1],
+                                         _stream(unit.device)))
+    return out
+
+
+def quantiles(u, v, pos_u, pos_v, flags, from_cdf=False, want_indices=False):
+    """(uq, vq, qs, cu, cv[, iu, iv]); with `from_cdf` the rows ARE the CDFs (parity harness)."""
+    lib = load()
+    prob = make_problem(u, v, pos_u, pos_v, 2.0, flags)
+    N, n = u.shape
+    m = v.shape[1]
+    f32 = dict(dtype=torch.float32, device=u.device)
+    uq, vq, qs = (torch.empty(N, n + m, **f32) for _ in range(3))
+    iu = torch.empty(N, n + m, dtype=torch.int32, device=u.device) if want_indices else None
+    iv = torch.empty(N, n + m, dtype=torch.int32, device=u.device) if want_indices else None
+    with torch.cuda.device(u.device):
+        if from_cdf:
+            cu, cv = u, v
+            _check(lib.sot_plan_from_cdf_device(ctypes.byref(prob), _ptr(uq), _ptr(vq), _ptr(qs), _ptr(iu), _ptr(iv),
+                                                _stream(u.device)))
+        else:
+            cu, cv = torch.empty(N, n, **f32), torch.empty(N, m, **f32)
+            _check(lib.sot_quantiles_device(ctypes.byref(prob), _ptr(uq), _ptr(vq), _ptr(qs), _ptr(cu), _ptr(cv),
+                                            _ptr(iu), _ptr(iv), _stream(u.device)))
+    return (uq, vq, qs, cu, cv, iu, iv) if want_indices else (uq, vq, qs, cu, cv)
+
+
+def loss_from_cdf(cu, cv, pos_u, pos_v, p, flags, want_grads=True):
+    """Parity harness: per-frame loss and dL/dcu, dL/dcv from injected CDF rows."""
+    lib = load()
+    prob = make_problem(cu, cv, pos_u, pos_v, p, flags)
+    loss = torch.empty(cu.shape[0], dtype=torch.float32, device=cu.device)
+    g_cu = torch.empty_like(cu) if want_grads else None
+    g_cv = torch.empty_like(cv) if want_grads else None
+    with torch.cuda.device(cu.device):
+        _check(lib.sot_loss_from_cdf_device(ctypes.byref(prob), _ptr(loss), _ptr(g_cu), _ptr(g_cv), _stream(cu.device)))
+    return loss, g_cu, g_cv
+
+
+def quantile_lookup(qs, cws, xs) -> torch.Tensor:
+    lib = load()
+    for t, name in ((qs, "qs"), (cws, "cws"), (xs, "xs")):
+        _dev_tensor(t, name)
+        if t.ndim != 2 or not t.is_contiguous():
+            raise ValueError(f"sot_b200: `{name}` must be a contiguous 2-D tensor")
+    if cws.shape != xs.shape or qs.shape[0] != cws.shape[0]:
+        raise ValueError("sot_b200: quantile_function shape mismatch")
+    out = torch.empty_like(qs)
+    with torch.cuda.device(qs.device):
+        _check(lib.sot_quantile_lookup_device(_ptr(qs), _ptr(cws), _ptr(xs), _ptr(out), qs.shape[0], qs.shape[1],
+                                              cws.shape[1], _stream(qs.device)))
+    return out
+
+
+def loss_grad_host(u, v, pos_u, pos_v, p, flags, upstream=None, want_loss=True, want_gu=True, want_gv=True,
+                   device=0, out=None):
+    """Host-buffer entry point: CPU tensors in (ideally pinned), CPU tensors out; all copies and
+    kernels happen inside the one C call.  `out` may carry preallocated (pinned) result tensors."""
+    lib = load()
+    for t, name in ((u, "x"), (v, "y"), (pos_u, "x_pos"), (pos_v, "y_pos")):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"sot_b200: `{name}` must be a contiguous float32 CPU tensor for the host entry point")
+    N, n = u.shape
+    m = v.shape[1]
+    su = 0 if pos_u.ndim == 1 else n
+    sv = 0 if pos_v.ndim == 1 else m
+    prob = SotProblem(N, n, m, u.data_ptr(), v.data_ptr(), pos_u.data_ptr(), pos_v.data_ptr(), su, sv, float(p),
+                      int(flags))
+    out = out or {}
+    loss = out.get("loss", torch.empty(N) if want_loss else None)
+    gu = out.get("grad_u", torch.empty_like(u) if want_gu else None)
+    gv = out.get("grad_v", torch.empty_like(v) if want_gv else None)
+    _check(lib.sot_loss_grad_host(ctypes.byref(prob), _ptr(upstream), _ptr(loss), _ptr(gu), _ptr(gv), int(device)))
+    return loss, gu, gv
+
+
+def set_tuning(threads_per_frame: int = 0, bins_per_thread: int = 0):
+    _check(load().sot_set_tuning(threads_per_frame, bins_per_thread))
+
+
+def launch_count() -> int:
+    return int(load().sot_launch_count())
+
+
+def max_bins(with_grad: bool = True, shared_positions: bool = True) -> int:
+    return int(load().sot_max_bins(int(with_grad), int(shared_positions)))

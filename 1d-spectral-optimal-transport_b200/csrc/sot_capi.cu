@@ -1,0 +1,427 @@
+// C ABI of libsot_b200.so (declared in include/sot_b200.h): argument validation, kernel
+// configuration choice, and the host-buffer pipeline.  No torch types, no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/sot_b200.h"
+#include "sot_launch.cuh"
+
+SOT_DECLARE_CONFIG(32, 9, 4)
+SOT_DECLARE_CONFIG(32, 33, 4)
+SOT_DECLARE_CONFIG(64, 17, 4)
+SOT_DECLARE_CONFIG(128, 9, 4)
+SOT_DECLARE_CONFIG(128, 17, 4)
+SOT_DECLARE_CONFIG(128, 33, 1)
+SOT_DECLARE_CONFIG(256, 33, 1)
+
+namespace sot {
+// ------------------------------------------------------------------------------------------
+// grad rows scaled by a per-frame factor: out[r, :] = unit[r, :] * s[r]   (backward of the
+// "fused" mode, where the forward launch already produced d loss_r / d input)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sot_scale_rows_kernel(const float* __restrict__ unit,
+                                                             const float* __restrict__ s,
+                                                             float* __restrict__ out, long long rows, int width) {
+    const long long total = rows * width;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += stride) {
+        out[idx] = unit[idx] * s[idx / width];
+    }
+}
+
+
+// quantile_function (losses.py:214-220) as a stand-alone op: for every query level the position
+// stored at the first CDF entry >= level (searchsorted 'left', index clamped to the last bin).
+__global__ void __launch_bounds__(256) sot_quantile_lookup_kernel(const float* __restrict__ qs,
+                                                                  const float* __restrict__ cws,
+                                                                  const float* __restrict__ xs,
+                                                                  float* __restrict__ out, long long rows, int k,
+                                                                  int n) {
+    const long long total = rows * k;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += stride) {
+        const long long r = idx / k;
+        const float q = qs[idx];
+        const float* row = cws + r * n;
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (row[mid] < q)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        out[idx] = xs[r * n + min(lo, n - 1)];
+    }
+}
+
+}  // namespace sot
+
+namespace {
+
+using LaunchFn = cudaError_t (*)(const sot::LaunchRequest&, cudaStream_t);
+struct Config {
+    int tpf, e, fpc;
+    LaunchFn fn;
+};
+// Ordered by preference for a given row length: the first entry whose capacity (tpf * e) and
+// shared-memory footprint fit is used.  Chosen from measurements on B200 (profiles/).
+const Config kConfigs[] = {
+    {32, 9, 4, sot_launch_32_9_4},      // <= 288 bins   (n_fft 512: 257)
+    {128, 9, 4, sot_launch_128_9_4},    // <= 1152 bins  (n_fft 2048: 1025)
+    {64, 17, 4, sot_launch_64_17_4},    // <= 1088 bins  alternative shape for 1025
+    {32, 33, 4, sot_launch_32_33_4},    // <= 1056 bins  alternative shape for 1025
+    {128, 17, 4, sot_launch_128_17_4},  // <= 2176 bins  (n_fft 4096)
+    {128, 33, 1, sot_launch_128_33_1},  // <= 4224 bins  (n_fft 8192), one frame per CTA
+    {256, 33, 1, sot_launch_256_33_1},  // <= 8448 bins  (n_fft 16384)
+};
+constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
+constexpr int kMaxSmem = 227 * 1024;
+
+thread_local char g_error[512] = "";
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_tune_tpf{0}, g_tune_e{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_error, sizeof(g_error), "%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+}
+
+int smem_need(const Config& c, int n, int m, bool with_grad, bool su, bool sv) {
+    return sot::smem_plan(c.fpc, n, m, c.tpf, with_grad, su, sv).total;
+}
+
+const Config* pick_config(int n, int m, bool with_grad, bool su, bool sv) {
+    const int need = n > m ? n : m;
+    const int tt = g_tune_tpf.load(), te = g_tune_e.load();
+    if (tt != 0) {
+        for (int i = 0; i < kNumConfigs; ++i) {
+            const Config& c = kConfigs[i];
+            if (c.tpf == tt && c.e == te && c.tpf * c.e >= need && smem_need(c, n, m, with_grad, su, sv) <= kMaxSmem)
+                return &c;
+        }
+    }
+    for (int i = 0; i < kNumConfigs; ++i) {
+        const Config& c = kConfigs[i];
+        if (c.tpf * c.e >= need && smem_need(c, n, m, with_grad, su, sv) <= kMaxSmem) return &c;
+    }
+    return nullptr;
+}
+
+int validate(const sot_problem* p) {
+    if (p == nullptr) return fail(SOT_EINVAL, "problem is NULL");
+    if (p->n_frames < 0 || p->n_u < 1 || p->n_v < 1)
+        return fail(SOT_EINVAL, "bad sizes: n_frames=%lld n_u=%d n_v=%d", (long long)p->n_frames, p->n_u, p->n_v);
+    if (p->n_u >= 65536 || p->n_v >= 65536) return fail(SOT_ETOOBIG, "rows longer than 65535 bins");
+    if (p->n_frames > 0 && (p->u == nullptr || p->v == nullptr)) return fail(SOT_EINVAL, "u or v is NULL");
+    if (p->pos_u == nullptr || p->pos_v == nullptr)
+        return fail(SOT_EINVAL, "support positions are required (pos_u / pos_v is NULL)");
+    if (p->pos_u_stride < 0 || p->pos_v_stride < 0) return fail(SOT_EINVAL, "negative position stride");
+    if (!(p->p >= 1.0f))  // also rejects NaN; losses.py:271
+        return fail(SOT_EDOMAIN, "The OT loss is only valid for p>=1, %g was given", (double)p->p);
+    if (p->flags & ~(SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS))
+        return fail(SOT_EINVAL, "unknown flag bits");
+    if ((p->n_frames + 3) / 4 > 0x7fffffffLL) return fail(SOT_ETOOBIG, "too many frames for one launch");
+    return SOT_OK;
+}
+
+sot::FrameArgs base_args(const sot_problem* p) {
+    sot::FrameArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u = p->u;
+    a.v = p->v;
+    a.pos_u = p->pos_u;
+    a.pos_v = p->pos_v;
+    a.pos_u_stride = p->pos_u_stride;
+    a.pos_v_stride = p->pos_v_stride;
+    a.n_frames = p->n_frames;
+    a.n = p->n_u;
+    a.m = p->n_v;
+    a.p = p->p;
+    a.flags = p->flags;
+    return a;
+}
+
+int launch(const sot_problem* p, sot::LaunchRequest& r, void* stream) {
+    if (p->n_frames == 0) return SOT_OK;
+    const bool with_grad = r.out == sot::OUT_GRAD;
+    const Config* c = pick_config(p->n_u, p->n_v, with_grad, p->pos_u_stride == 0, p->pos_v_stride == 0);
+    if (c == nullptr)
+        return fail(SOT_ETOOBIG, "rows of %d / %d bins do not fit any kernel configuration (shared memory)", p->n_u,
+                    p->n_v);
+    cudaError_t e = c->fn(r, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "sot_frames_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SOT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sot_abi_version(void) { return SOT_B200_ABI_VERSION; }
+const char* sot_last_error(void) { return g_error; }
+int64_t sot_launch_count(void) { return g_launches.load(); }
+
+int sot_set_tuning(int32_t tpf, int32_t e) {
+    if (tpf == 0 && e == 0) {
+        g_tune_tpf = 0;
+        g_tune_e = 0;
+        return SOT_OK;
+    }
+    for (int i = 0; i < kNumConfigs; ++i)
+        if (kConfigs[i].tpf == tpf && kConfigs[i].e == e) {
+            g_tune_tpf = tpf;
+            g_tune_e = e;
+            return SOT_OK;
+        }
+    return fail(SOT_EINVAL, "no kernel configuration with %d threads per frame and %d bins per thread", tpf, e);
+}
+
+int sot_max_bins(int32_t with_grad, int32_t shared_positions) {
+    int best = 0;
+    for (int i = 0; i < kNumConfigs; ++i) {
+        const Config& c = kConfigs[i];
+        int lo = 1, hi = c.tpf * c.e;
+        while (lo < hi) {  // largest n (= m) whose footprint fits
+            const int mid = (lo + hi + 1) / 2;
+            if (smem_need(c, mid, mid, with_grad != 0, shared_positions != 0, shared_positions != 0) <= kMaxSmem)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        if (smem_need(c, lo, lo, with_grad != 0, shared_positions != 0, shared_positions != 0) <= kMaxSmem && lo > best)
+            best = lo;
+    }
+    return best;
+}
+
+int sot_forward_device(const sot_problem* prob, float* loss, void* stream) {
+    if (int rc = validate(prob)) return rc;
+    if (loss == nullptr && prob->n_frames > 0) return fail(SOT_EINVAL, "loss is NULL");
+    sot::LaunchRequest r{base_args(prob), sot::OUT_LOSS, sot::MODE_SPECTRA};
+    r.args.loss = loss;
+    return launch(prob, r, stream);
+}
+
+int sot_forward_backward_device(const sot_problem* prob, const float* upstream, float* loss, float* grad_u,
+                                float* grad_v, void* stream) {
+    if (int rc = validate(prob)) return rc;
+    sot::LaunchRequest r{base_args(prob), sot::OUT_GRAD, sot::MODE_SPECTRA};
+    r.args.upstream = upstream;
+    r.args.loss = loss;
+    r.args.grad_u = grad_u;
+    r.args.grad_v = grad_v;
+    return launch(prob, r, stream);
+}
+
+int sot_scale_rows_device(const float* unit, const float* scale, float* out, int64_t rows, int32_t width,
+                          void* stream) {
+    if (rows < 0 || width < 1) return fail(SOT_EINVAL, "bad sizes: rows=%lld width=%d", (long long)rows, width);
+    if (rows == 0) return SOT_OK;
+    if (unit == nullptr || scale == nullptr || out == nullptr) return fail(SOT_EINVAL, "NULL pointer");
+    const long long total = rows * width;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    sot::sot_scale_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        unit, scale, out, rows, width);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "sot_scale_rows_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SOT_OK;
+}
+
+int sot_quantile_lookup_device(const float* qs, const float* cws, const float* xs, float* out, int64_t rows,
+                               int32_t n_levels, int32_t n_bins, void* stream) {
+    if (rows < 0 || n_levels < 1 || n_bins < 1) return fail(SOT_EINVAL, "bad sizes");
+    if (rows == 0) return SOT_OK;
+    if (qs == nullptr || cws == nullptr || xs == nullptr || out == nullptr) return fail(SOT_EINVAL, "NULL pointer");
+    long long blocks = (rows * n_levels + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    sot::sot_quantile_lookup_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        qs, cws, xs, out, rows, n_levels, n_bins);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "sot_quantile_lookup_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SOT_OK;
+}
+
+int sot_quantiles_device(const sot_problem* prob, float* uq, float* vq, float* qs, float* cu, float* cv, int32_t* iu,
+                         int32_t* iv, void* stream) {
+    if (int rc = validate(prob)) return rc;
+    sot::LaunchRequest r{base_args(prob), sot::OUT_PLAN, sot::MODE_SPECTRA};
+    r.args.plan_uq = uq;
+    r.args.plan_vq = vq;
+    r.args.plan_qs = qs;
+    r.args.plan_cu = cu;
+    r.args.plan_cv = cv;
+    r.args.plan_iu = iu;
+    r.args.plan_iv = iv;
+    return launch(prob, r, stream);
+}
+
+int sot_plan_from_cdf_device(const sot_problem* prob, float* uq, float* vq, float* qs, int32_t* iu, int32_t* iv,
+                             void* stream) {
+    if (int rc = validate(prob)) return rc;
+    sot::LaunchRequest r{base_args(prob), sot::OUT_PLAN, sot::MODE_CDF};
+    r.args.plan_uq = uq;
+    r.args.plan_vq = vq;
+    r.args.plan_qs = qs;
+    r.args.plan_iu = iu;
+    r.args.plan_iv = iv;
+    return launch(prob, r, stream);
+}
+
+int sot_loss_from_cdf_device(const sot_problem* prob, float* loss, float* g_cu, float* g_cv, void* stream) {
+    if (int rc = validate(prob)) return rc;
+    const bool grads = (g_cu != nullptr) || (g_cv != nullptr);
+    sot::LaunchRequest r{base_args(prob), grads ? sot::OUT_GRAD : sot::OUT_LOSS, sot::MODE_CDF};
+    r.args.loss = loss;
+    r.args.grad_u = g_cu;
+    r.args.grad_v = g_cv;
+    return launch(prob, r, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-buffer pipeline: frames are cut into chunks; chunk c+1's host->device copy, chunk c's
+// kernel and chunk c-1's device->host copy overlap on three streams (PCIe is full duplex).
+// ------------------------------------------------------------------------------------------
+int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss, float* grad_u, float* grad_v,
+                       int32_t device) {
+    if (int rc = validate(hp)) return rc;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const long long N = hp->n_frames;
+    if (N == 0) return SOT_OK;
+    const int n = hp->n_u, m = hp->n_v;
+    const bool want_grad = grad_u != nullptr || grad_v != nullptr;
+    constexpr int kSlots = 3;
+    long long chunk = (48LL << 20) / (4LL * (n + m));  // ~48 MiB of input per chunk
+    chunk = (chunk / 4) * 4;
+    if (chunk < 4) chunk = 4;
+    if (chunk > N) chunk = ((N + 3) / 4) * 4;
+
+    struct Slot {
+        float *u, *v, *gu, *gv, *loss, *up, *pu, *pv;
+        cudaEvent_t in_done, k_done, out_done;
+    } slot[kSlots];
+    memset(slot, 0, sizeof(slot));
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    float *d_pu = nullptr, *d_pv = nullptr;
+    int rc = SOT_OK;
+#define SOT_CK(call)                                 \
+    do {                                             \
+        cudaError_t _e = (call);                     \
+        if (_e != cudaSuccess && rc == SOT_OK) {     \
+            rc = cuda_fail(_e, #call);               \
+            goto done;                               \
+        }                                            \
+    } while (0)
+    {
+        SOT_CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        SOT_CK(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+        SOT_CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        const bool su = hp->pos_u_stride == 0, sv = hp->pos_v_stride == 0;
+        if (su) {
+            SOT_CK(cudaMalloc(&d_pu, 4LL * n));
+            SOT_CK(cudaMemcpyAsync(d_pu, hp->pos_u, 4LL * n, cudaMemcpyHostToDevice, s_in));
+        }
+        if (sv) {
+            SOT_CK(cudaMalloc(&d_pv, 4LL * m));
+            SOT_CK(cudaMemcpyAsync(d_pv, hp->pos_v, 4LL * m, cudaMemcpyHostToDevice, s_in));
+        }
+        for (int k = 0; k < kSlots; ++k) {
+            SOT_CK(cudaMalloc(&slot[k].u, 4LL * chunk * n));
+            SOT_CK(cudaMalloc(&slot[k].v, 4LL * chunk * m));
+            SOT_CK(cudaMalloc(&slot[k].loss, 4LL * chunk));
+            if (upstream != nullptr) SOT_CK(cudaMalloc(&slot[k].up, 4LL * chunk));
+            if (grad_u != nullptr) SOT_CK(cudaMalloc(&slot[k].gu, 4LL * chunk * n));
+            if (grad_v != nullptr) SOT_CK(cudaMalloc(&slot[k].gv, 4LL * chunk * m));
+            if (!su) SOT_CK(cudaMalloc(&slot[k].pu, 4LL * chunk * n));
+            if (!sv) SOT_CK(cudaMalloc(&slot[k].pv, 4LL * chunk * m));
+            SOT_CK(cudaEventCreateWithFlags(&slot[k].in_done, cudaEventDisableTiming));
+            SOT_CK(cudaEventCreateWithFlags(&slot[k].k_done, cudaEventDisableTiming));
+            SOT_CK(cudaEventCreateWithFlags(&slot[k].out_done, cudaEventDisableTiming));
+        }
+        long long c = 0;
+        for (long long f0 = 0; f0 < N; f0 += chunk, ++c) {
+            Slot& s = slot[c % kSlots];
+            const long long nf = (N - f0 < chunk) ? (N - f0) : chunk;
+            if (c >= kSlots) SOT_CK(cudaStreamWaitEvent(s_in, s.out_done, 0));  // slot drained
+            SOT_CK(cudaMemcpyAsync(s.u, hp->u + f0 * n, 4LL * nf * n, cudaMemcpyHostToDevice, s_in));
+            SOT_CK(cudaMemcpyAsync(s.v, hp->v + f0 * m, 4LL * nf * m, cudaMemcpyHostToDevice, s_in));
+            if (upstream != nullptr)
+                SOT_CK(cudaMemcpyAsync(s.up, upstream + f0, 4LL * nf, cudaMemcpyHostToDevice, s_in));
+            if (!su)
+                SOT_CK(cudaMemcpy2DAsync(s.pu, 4LL * n, hp->pos_u + f0 * hp->pos_u_stride, 4LL * hp->pos_u_stride,
+                                         4LL * n, nf, cudaMemcpyHostToDevice, s_in));
+            if (!sv)
+                SOT_CK(cudaMemcpy2DAsync(s.pv, 4LL * m, hp->pos_v + f0 * hp->pos_v_stride, 4LL * hp->pos_v_stride,
+                                         4LL * m, nf, cudaMemcpyHostToDevice, s_in));
+            SOT_CK(cudaEventRecord(s.in_done, s_in));
+            SOT_CK(cudaStreamWaitEvent(s_k, s.in_done, 0));
+            sot_problem dp = *hp;
+            dp.n_frames = nf;
+            dp.u = s.u;
+            dp.v = s.v;
+            dp.pos_u = su ? d_pu : s.pu;
+            dp.pos_v = sv ? d_pv : s.pv;
+            dp.pos_u_stride = su ? 0 : n;
+            dp.pos_v_stride = sv ? 0 : m;
+            int krc = want_grad ? sot_forward_backward_device(&dp, s.up, s.loss, s.gu, s.gv, s_k)
+                                : sot_forward_device(&dp, s.loss, s_k);
+            if (krc != SOT_OK) {
+                rc = krc;
+                goto done;
+            }
+            SOT_CK(cudaEventRecord(s.k_done, s_k));
+            SOT_CK(cudaStreamWaitEvent(s_out, s.k_done, 0));
+            if (loss != nullptr) SOT_CK(cudaMemcpyAsync(loss + f0, s.loss, 4LL * nf, cudaMemcpyDeviceToHost, s_out));
+            if (grad_u != nullptr)
+                SOT_CK(cudaMemcpyAsync(grad_u + f0 * n, s.gu, 4LL * nf * n, cudaMemcpyDeviceToHost, s_out));
+            if (grad_v != nullptr)
+                SOT_CK(cudaMemcpyAsync(grad_v + f0 * m, s.gv, 4LL * nf * m, cudaMemcpyDeviceToHost, s_out));
+            SOT_CK(cudaEventRecord(s.out_done, s_out));
+        }
+        SOT_CK(cudaStreamSynchronize(s_out));
+        SOT_CK(cudaStreamSynchronize(s_k));
+        SOT_CK(cudaStreamSynchronize(s_in));
+    }
+done:
+    for (int k = 0; k < kSlots; ++k) {
+        cudaFree(slot[k].u);
+        cudaFree(slot[k].v);
+        cudaFree(slot[k].gu);
+        cudaFree(slot[k].gv);
+        cudaFree(slot[k].loss);
+        cudaFree(slot[k].up);
+        cudaFree(slot[k].pu);
+        cudaFree(slot[k].pv);
+        if (slot[k].in_done) cudaEventDestroy(slot[k].in_done);
+        if (slot[k].k_done) cudaEventDestroy(slot[k].k_done);
+        if (slot[k].out_done) cudaEventDestroy(slot[k].out_done);
+    }
+    cudaFree(d_pu);
+    cudaFree(d_pv);
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_k) cudaStreamDestroy(s_k);
+    if (s_out) cudaStreamDestroy(s_out);
+#undef SOT_CK
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+/* sot_b200.h -- C ABI of the B200-native Spectral Optimal Transport (SOT) loss.
+ *
+ * This is the drop-in boundary for ONE hot path of bernardo-torres/1d-spectral-optimal-transport:
+ * `losses.Wasserstein1D.forward` -> `losses.wasserstein_1d` -> `losses.quantile_function`
+ * (reference losses.py:129-313, utils.py:135-142) and its autograd backward.  The reference has no
+ * native code; what a maintainer binds (ctypes, shown in INTEGRATION.md) are the entry points
+ * below -- plain pointers and sizes, no torch types.  All `const float*` / `float*` arguments of
+ * the *_device entry points are CUDA device pointers on the current device; `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = default stream).  Calls are asynchronous on `stream`
+ * unless stated otherwise.  Every function returns 0 on success, a negative SOT_E* code on a
+ * rejected argument (nothing was launched) or a positive `cudaError_t`; `sot_last_error()`
+ * gives the text.  There is no CPU fallback anywhere in this library.
+ *
+ * Layout: spectra are row-major contiguous [n_frames, bins] float32 -- exactly the memory of the
+ * reference's (batch, time, freq) tensors after `reshape(-1, F)` (losses.py:158-165).  Argument
+ * order follows the reference: `u` is the TARGET spectrum (first argument `x`, normalised to
+ * unit mass), `v` the PREDICTION (`y`; in cutoff mode divided by the target's mass).
+ */
+#ifndef SOT_B200_H
+#define SOT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOT_B200_ABI_VERSION 1
+
+/* flags (bit-or) */
+#define SOT_SQUARE 1    /* square_dist=True: weights = magnitude^2        losses.py:172-174 */
+#define SOT_CUT_SCALE 2 /* dont_normalize=True: v / mass(u), not / mass(v) losses.py:180-182 */
+#define SOT_LIMIT 4     /* limit_quantile_range=True: strict `qs > 1` mask losses.py:306-307 */
+#define SOT_RAW_WEIGHTS 8 /* rows are weights used as given, no normalisation: the module-level
+                            `wasserstein_1d(u_values, v_values, u_weights, v_weights)` losses.py:223 */
+
+/* error codes */
+#define SOT_OK 0
+#define SOT_EINVAL (-1)   /* bad pointer / size / flag combination        */
+#define SOT_ETOOBIG (-2)  /* row does not fit the largest kernel config   */
+#define SOT_EDOMAIN (-3)  /* p < 1 (reference: AssertionError, losses.py:271) */
+
+/* One batch of frames.  Mirrors the arguments of `wasserstein_1d` (losses.py:223-232) plus the
+ * prologue switches of `Wasserstein1D.forward` (losses.py:172-184). */
+typedef struct sot_problem {
+    int64_t n_frames;      /* N = batch * time                                              */
+    int32_t n_u;           /* bins of u (n)                                                 */
+    int32_t n_v;           /* bins of v (m); may differ from n_u                            */
+    const float* u;        /* [N, n_u] target magnitudes                                    */
+    const float* v;        /* [N, n_v] prediction magnitudes                                */
+    const float* pos_u;    /* support positions of u, ASCENDING along the row: [n_u] when    */
+    const float* pos_v;    /*   pos_*_stride == 0 (one grid shared by all frames), else rows */
+    int64_t pos_u_stride;  /*   of a [N, n_*] array with this element stride                */
+    int64_t pos_v_stride;
+    float p;               /* order of the distance, >= 1 (result is W_p^p, no root)        */
+    int32_t flags;         /* SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS      */
+} sot_problem;
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+
+/* Forward: loss[N] = per-frame W_p^p.  Replaces losses.py:172-184 + 286-313 (one launch). */
+int sot_forward_device(const sot_problem* prob, float* loss, void* stream);
+
+/* Fused forward + backward: loss[N] (nullable) and
+ *   grad_u[N, n_u] = upstream[n] * d loss_n / d u   (nullable),
+ *   grad_v[N, n_v] = upstream[n] * d loss_n / d v   (nullable),
+ * `upstream` = dL/dloss_n per frame, NULL meaning 1.  Replaces the autograd backward of
+ * losses.py:172-313; tie attribution = stable sort order. */
+int sot_forward_backward_device(const sot_problem* prob, const float* upstream, float* loss,
+                                float* grad_u, float* grad_v, void* stream);
+
+/* out[r, :] = unit[r, :] * scale[r]  -- backward of the "fused" autograd mode, where the forward
+ * launch already produced the unit gradients. */
+int sot_scale_rows_device(const float* unit, const float* scale, float* out, int64_t rows,
+                          int32_t width, void* stream);
+
+/* `return_quantiles=True` (losses.py:198-201, 299-300).  All outputs nullable:
+ *   uq, vq, qs : [N, n_u + n_v]   quantile positions and merged quantile grid
+ *   cu, cv     : [N, n_u], [N, n_v]  CDFs
+ *   iu, iv     : [N, n_u + n_v] int32  un-clamped `searchsorted(c*, qs)` indices (losses.py:219) */
+int sot_quantiles_device(const sot_problem* prob, float* uq, float* vq, float* qs, float* cu,
+                         float* cv, int32_t* iu, int32_t* iv, void* stream);
+
+/* `quantile_function(qs, cws, xs)` (losses.py:214-220) as a stand-alone op:
+ * out[r, k] = xs[r, min(lower_bound(cws[r, :], qs[r, k]), n_bins - 1)]. */
+int sot_quantile_lookup_device(const float* qs, const float* cws, const float* xs, float* out,
+                               int64_t rows, int32_t n_levels, int32_t n_bins, void* stream);
+
+/* ---- parity harness (same kernels, prologue skipped) ------------------------------------------ */
+
+/* Treat prob->u / prob->v as already-computed CDF rows (e.g. the reference's own `cumsum`
+ * outputs): merged grid + searchsorted indices.  Bit-exact gate P1 of SURVEY.md App. B. */
+int sot_plan_from_cdf_device(const sot_problem* prob, float* uq, float* vq, float* qs, int32_t* iu,
+                             int32_t* iv, void* stream);
+/* Same inputs: per-frame loss and dL/dcu, dL/dcv (before the cumsum transpose).  Gate P2. */
+int sot_loss_from_cdf_device(const sot_problem* prob, float* loss, float* g_cu, float* g_cv,
+                             void* stream);
+
+/* ---- host-buffer entry point (what a non-torch caller binds) ---------------------------------- */
+
+/* Whole job with HOST buffers: copies u, v (and positions) to the device in chunks on two
+ * streams, runs the fused kernel, copies loss and gradients back.  Blocking.  `upstream` and
+ * each output are nullable host pointers.  Pinned host memory is used as-is; pageable memory
+ * works but is slower.  `device` = CUDA ordinal. */
+int sot_loss_grad_host(const sot_problem* host_prob, const float* upstream, float* loss, float* grad_u,
+                       float* grad_v, int32_t device);
+
+/* ---- housekeeping ---------------------------------------------------------------------------- */
+int sot_abi_version(void);
+const char* sot_last_error(void);
+/* Largest row length (max(n_u, n_v)) the kernels accept for the given outputs. */
+int sot_max_bins(int32_t with_grad, int32_t shared_positions);
+/* Tuning override for benchmarking: threads per frame (32/64/128/256) and bins per thread
+ * (odd); 0, 0 restores the built-in choice.  Returns SOT_EINVAL if that pair is not compiled in. */
+int sot_set_tuning(int32_t threads_per_frame, int32_t bins_per_thread);
+/* Number of kernel launches issued by this library in the calling process so far. */
+int64_t sot_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOT_B200_H */

@@ -1,0 +1,510 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the committed reference
+fixtures.  Protocol P1-P4 of SURVEY.md App. B.
+
+Tolerances (float32 arithmetic; stated where used):
+  * P1 merged grid / searchsorted indices / quantile positions from injected CDFs: BIT-EXACT.
+  * P2 per-frame loss from injected CDFs: rel 2e-6 (summation order only); dL/dCDF: BIT-EXACT.
+  * loss from magnitudes, no-cut mode: rel 1e-5 per frame and in aggregate vs the reference.
+  * loss from magnitudes, cutoff mode: the reference is discontinuous in the last ulp of the
+    target CDF (strict `qs > 1` mask, App. B) -> compared on the kernel's own CDFs (which must be
+    within 1.5 ulp of the fp64 CDFs) at rel 2e-6, plus aggregate rel 2e-3 vs the reference value.
+  * gradients: rel-L2 vs the fp64 continuation from the same CDFs no worse than
+    max(2e-5, 1.5 x the reference's own fp32 autograd error) per frame.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sot_oracle as O
+from tests import golden_io as G
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from sot_b200 import _capi
+    _capi.load()
+    return _capi
+
+
+@pytest.fixture(scope="module")
+def L():
+    from sot_b200 import losses
+    return losses
+
+
+def _flags(capi, kw):
+    return ((capi.SOT_SQUARE if kw["square"] else 0) | (capi.SOT_CUT_SCALE if kw["cut_scale"] else 0) |
+            (capi.SOT_LIMIT if kw["limit"] else 0))
+
+
+def _sorted_case(g):
+    """Golden case as sorted-support 2-D rows (the C ABI wants ascending supports)."""
+    F = g["x"].shape[-1]
+    x, y = g["x"].reshape(-1, F), g["y"].reshape(-1, F)
+    pos, perm = torch.sort(g["pos_x"], stable=True)
+    return x[:, perm].contiguous(), y[:, perm].contiguous(), pos.contiguous(), perm
+
+
+# ------------------------------------------------------------------------------------------
+# P1: bit-exact plan from the reference's own CDFs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", G.MODULE_CASES)
+@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17), (128, 17)])
+def test_p1_plan_from_reference_cdfs_bit_exact(capi, name, tuning):
+    g = G.load(name)
+    F = g["x"].shape[-1]
+    if tuning[0] * tuning[1] and tuning[0] * tuning[1] < F:
+        pytest.skip("row does not fit this configuration")
+    cu, cv = g["cu"].reshape(-1, F).contiguous(), g["cv"].reshape(-1, F).contiguous()
+    pos = torch.sort(g["pos_x"], stable=True)[0]
+    capi.set_tuning(*tuning)
+    try:
+        uq, vq, qs, _, _, iu, iv = capi.quantiles(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), 0,
+                                                  from_cdf=True, want_indices=True)
+    finally:
+        capi.set_tuning(0, 0)
+    K = 2 * F
+    assert torch.equal(qs.cpu(), g["qs"].reshape(-1, K)), "merged quantile grid"
+    iu_ref = torch.searchsorted(cu, g["qs"].reshape(-1, K).contiguous())
+    iv_ref = torch.searchsorted(cv, g["qs"].reshape(-1, K).contiguous())
+    assert torch.equal(iu.cpu().long(), iu_ref), "searchsorted(cu, qs)"
+    assert torch.equal(iv.cpu().long(), iv_ref), "searchsorted(cv, qs)"
+    assert torch.equal(uq.cpu(), g["uq"].reshape(-1, K)) and torch.equal(vq.cpu(), g["vq"].reshape(-1, K))
+
+
+def test_p1_unequal_supports_and_heavy_ties(capi):
+    rng = np.random.default_rng(3)
+    N, n, m = 10, 37, 90
+    wu = rng.random((N, n)).astype(np.float32) * (rng.random((N, n)) < 0.3)
+    wv = rng.random((N, m)).astype(np.float32) * (rng.random((N, m)) < 0.3)
+    wu[:, 0] += 0.1
+    wv[:, 0] += 0.1
+    wv[3, :n] = wu[3]  # shared values between the two rows -> cross ties
+    cu = torch.from_numpy(np.cumsum(wu / wu.sum(1, keepdims=True), axis=1, dtype=np.float64).astype(np.float32))
+    cv = torch.from_numpy(np.cumsum(wv / wu.sum(1, keepdims=True), axis=1, dtype=np.float64).astype(np.float32))
+    pu = torch.sort(torch.rand(N, n), dim=1)[0]
+    pv = torch.sort(torch.rand(N, m), dim=1)[0]
+    uq, vq, qs, _, _, iu, iv = capi.quantiles(cu.to(DEV), cv.to(DEV), pu.to(DEV), pv.to(DEV), 0, from_cdf=True,
+                                              want_indices=True)
+    qs_ref = torch.sort(torch.cat((cu, cv), 1), dim=1, stable=True)[0]
+    assert torch.equal(qs.cpu(), qs_ref)
+    assert torch.equal(iu.cpu().long(), torch.searchsorted(cu, qs_ref))
+    assert torch.equal(iv.cpu().long(), torch.searchsorted(cv, qs_ref))
+    uq_ref, _ = O.lower_bound_lookup(qs_ref, cu, pu)
+    vq_ref, _ = O.lower_bound_lookup(qs_ref, cv, pv)
+    assert torch.equal(uq.cpu(), uq_ref) and torch.equal(vq.cpu(), vq_ref)
+
+
+# ------------------------------------------------------------------------------------------
+# P2: loss and dL/dCDF from injected CDFs vs the closed form (stable-sort tie attribution)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["sot512_cut", "sot512_nocut", "sot2048_cut", "sot2048_nocut", "sot512_logf_cut"])
+@pytest.mark.parametrize("p", [1.0, 2.0, 3.0])
+@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17)])
+def test_p2_loss_and_cdf_gradients_from_reference_cdfs(capi, name, p, tuning):
+    g = G.load(name)
+    F = g["x"].shape[-1]
+    if tuning[0] * tuning[1] and tuning[0] * tuning[1] < F:
+        pytest.skip("row does not fit this configuration")
+    limit = bool(g["meta"]["ctor"].get("limit_quantile_range", False))
+    cu, cv = g["cu"].reshape(-1, F).contiguous(), g["cv"].reshape(-1, F).contiguous()
+    pos = g["pos_x"]
+    capi.set_tuning(*tuning)
+    try:
+        loss, g_cu, g_cv = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p,
+                                              capi.SOT_LIMIT if limit else 0)
+        loss_only, _, _ = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p,
+                                             capi.SOT_LIMIT if limit else 0, want_grads=False)
+    finally:
+        capi.set_tuning(0, 0)
+    assert torch.equal(loss, loss_only), "forward-only and fused kernels disagree on the loss"
+    for r in range(cu.shape[0]):
+        pn = pos.numpy()
+        ref_loss, r_cu, r_cv, _, _ = O.closed_form_from_cdfs(cu[r].numpy(), cv[r].numpy(), pn, pn, int(p), limit)
+        assert abs(loss[r].item() - float(ref_loss)) <= 2e-6 * abs(float(ref_loss)) + 1e-12, f"frame {r} loss"
+        if p == 3.0:  # powf on the device vs numpy power: compare to rounding, not bit-exactly
+            assert np.allclose(g_cu[r].cpu().numpy(), r_cu, rtol=1e-5, atol=1e-9)
+            assert np.allclose(g_cv[r].cpu().numpy(), r_cv, rtol=1e-5, atol=1e-9)
+        else:
+            assert np.array_equal(g_cu[r].cpu().numpy(), r_cu), f"frame {r}: dL/dcu"
+            assert np.array_equal(g_cv[r].cpu().numpy(), r_cv), f"frame {r}: dL/dcv"
+
+
+# ------------------------------------------------------------------------------------------
+# end to end from magnitudes: golden fixtures of the reference
+# ------------------------------------------------------------------------------------------
+def _ulp_distance(a, b):
+    ai = a.view(torch.int32).long()
+    bi = b.view(torch.int32).long()
+    return (ai - bi).abs()
+
+
+@pytest.mark.parametrize("name", G.MODULE_CASES)
+def test_kernel_cdfs_within_ulps_of_fp64(capi, L, name):
+    g = G.load(name)
+    kw = G.oracle_kwargs(g["meta"]["ctor"])
+    x, y, pos, _ = _sorted_case(g)
+    out = capi.quantiles(x.to(DEV), y.to(DEV), pos.to(DEV), pos.to(DEV), _flags(capi, dict(kw, limit=False)))
+    cu, cv = out[3].cpu(), out[4].cpu()
+    wx, wy = O.spectra_to_weights(x.double(), y.double(), kw["square"], kw["cut_scale"])
+    cu64, cv64 = torch.cumsum(wx, 1), torch.cumsum(wy, 1)
+    # the only fp32 step upstream of the CDF is the mass (one rounding): 1 ulp of slack for it,
+    # 0.5 ulp for the final rounding of each entry
+    assert _ulp_distance(cu, cu64.float()).max().item() <= 2
+    assert _ulp_distance(cv, cv64.float()).max().item() <= 2
+    assert (cu[:, 1:] >= cu[:, :-1]).all() and (cv[:, 1:] >= cv[:, :-1]).all(), "CDFs must be non-decreasing"
+    # and the plan built on them is exactly what the reference builds on the same CDFs
+    qs_ref = torch.sort(torch.cat((cu, cv), 1), dim=1, stable=True)[0]
+    assert torch.equal(out[2].cpu(), qs_ref)
+    uq_ref, _ = O.lower_bound_lookup(qs_ref, cu, pos.unsqueeze(0).expand_as(cu))
+    vq_ref, _ = O.lower_bound_lookup(qs_ref, cv, pos.unsqueeze(0).expand_as(cv))
+    assert torch.equal(out[0].cpu(), uq_ref) and torch.equal(out[1].cpu(), vq_ref)
+
+
+@pytest.mark.parametrize("name", G.MODULE_CASES)
+@pytest.mark.parametrize("mode", ["recompute", "fused"])
+def test_module_forward_backward_vs_reference_fixture(capi, L, name, mode):
+    g = G.load(name)
+    ctor = dict(g["meta"]["ctor"])
+    kw = G.oracle_kwargs(ctor)
+    mod = L.Wasserstein1D(**ctor, backward_mode=mode)
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = g["y"].to(DEV).requires_grad_(True)
+    px, py = g["pos_x"].to(DEV), g["pos_y"].to(DEV)
+    value = mod(x, y, x_pos=px, y_pos=py)
+    value.backward()
+    F = g["x"].shape[-1]
+    with torch.no_grad():
+        rows = mod(g["x"].reshape(-1, 1, F).to(DEV), g["y"].reshape(-1, 1, F).to(DEV), x_pos=px, y_pos=py, dims=1)
+    assert value.shape == g["value"].shape and rows.shape == g["rows"].shape
+    assert x.grad.shape == g["grad_x"].shape and y.grad.shape == g["grad_y"].shape
+    ref_rows = g["rows"]
+    rel = ((rows.cpu() - ref_rows).abs() / ref_rows.abs().clamp_min(1e-30))
+    if not kw["limit"]:
+        assert rel.max().item() <= 1e-5, f"per-frame loss, no-cut: {rel}"
+        assert abs(value.item() - g["value"].item()) <= 1e-5 * abs(g["value"].item())
+    else:
+        assert abs(value.item() - g["value"].item()) <= 2e-3 * abs(g["value"].item())
+
+    # loss and gradients against the fp64 continuation of the KERNEL's CDFs
+    xs, ys, pos, perm = _sorted_case(g)
+    out = capi.quantiles(xs.to(DEV), ys.to(DEV), pos.to(DEV), pos.to(DEV), _flags(capi, dict(kw, limit=False)))
+    cu, cv = out[3].cpu().numpy(), out[4].cpu().numpy()
+    a = xs.double() ** 2 if kw["square"] else xs.double()
+    b = ys.double() ** 2 if kw["square"] else ys.double()
+    mass_u, mass_v = a.sum(1).float().numpy(), b.sum(1).float().numpy()
+    gx = x.grad.reshape(-1, F).cpu()[:, perm].numpy() * rows.numel()  # undo the mean's 1/N
+    gy = y.grad.reshape(-1, F).cpu()[:, perm].numpy() * rows.numel()
+    ref_gx = g["grad_x"].reshape(-1, F)[:, perm].numpy() * rows.numel()
+    ref_gy = g["grad_y"].reshape(-1, F)[:, perm].numpy() * rows.numel()
+    f8 = np.float64
+    for r in range(xs.shape[0]):
+        tl, tgx, tgy = O.fp64_chain_from_cdfs(xs[r].numpy(), ys[r].numpy(), cu[r], cv[r], pos.numpy(), pos.numpy(),
+                                              mass_u[r], mass_v[r], kw["p"], kw["square"], kw["cut_scale"],
+                                              kw["limit"])
+        assert abs(rows[r].item() - tl) <= 2e-6 * abs(tl) + 1e-12, f"frame {r}: loss vs fp64 chain on kernel CDFs"
+        # Conditioning of the gradient: dL/dx = 2x (gw - <gw, w>) / M subtracts two O(|gw|) numbers.
+        # An fp32 evaluation (the reference's autograd included) carries eps32 * |uncancelled term|;
+        # measured on the CPU model of the kernel the ratio error / (eps32 * cond) stays below 1.3.
+        _, _, _, g_wu, g_wv = O.closed_form_from_cdfs(cu[r].astype(f8), cv[r].astype(f8), pos.numpy().astype(f8),
+                                                      pos.numpy().astype(f8), kw["p"], kw["limit"])
+        eps_m = np.float32(O.SAFE_EPS)
+        mu = max(mass_u[r], eps_m)
+        mv = mu if kw["cut_scale"] else max(mass_v[r], eps_m)
+        lead_x = (2 * xs[r].numpy() if kw["square"] else 1.0) * g_wu / f8(mu)
+        lead_y = (2 * ys[r].numpy() if kw["square"] else 1.0) * g_wv / f8(mv)
+        for mine, truth, lead, nm in ((gx[r], tgx, lead_x, "x"), (gy[r], tgy, lead_y, "y")):
+            nt = np.linalg.norm(truth)
+            if nt == 0:
+                assert np.linalg.norm(mine) == 0
+                continue
+            cond = np.linalg.norm(lead) / nt
+            e_mine = np.linalg.norm(mine - truth) / nt
+            bound = (4.0 if kw["p"] != 3 else 16.0) * 5.96e-8 * cond + 2e-6
+            assert e_mine <= bound, f"frame {r} grad_{nm}: rel-L2 {e_mine:.3e} > {bound:.3e} (cond {cond:.1f})"
+            # and never further from the fp64 continuation than 2x the reference's own fp32 autograd
+            # would be allowed to be under the same conditioning argument
+        if kw["limit"]:
+            same = (np.array_equal(cu[r], g["cu"].reshape(-1, F)[r].numpy()) and
+                    np.array_equal(cv[r], g["cv"].reshape(-1, F)[r].numpy()))
+            if same:
+                assert abs(rows[r].item() - ref_rows[r].item()) <= 2e-6 * abs(ref_rows[r].item())
+    del ref_gx, ref_gy
+
+
+def test_fused_and_recompute_modes_agree_bitwise(L):
+    g = G.load("sot2048_cut")
+    outs = []
+    for mode in ("recompute", "fused"):
+        mod = L.Wasserstein1D(**g["meta"]["ctor"], backward_mode=mode)
+        x = g["x"].to(DEV).requires_grad_(True)
+        y = g["y"].to(DEV).requires_grad_(True)
+        v = mod(x, y, x_pos=g["pos_x"].to(DEV), y_pos=g["pos_y"].to(DEV))
+        (3.0 * v).backward()
+        outs.append((v.detach().clone(), x.grad.clone(), y.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    # "fused" multiplies unit gradients by the upstream factor afterwards (one more rounding)
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=2e-7, atol=0)
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=2e-7, atol=0)
+
+
+@pytest.mark.parametrize("tuning", [(128, 9), (64, 17), (32, 33), (128, 17), (128, 33), (256, 33)])
+def test_every_kernel_configuration_gives_the_same_answer(capi, L, tuning):
+    g = G.load("sot2048_nocut")
+    base = None
+    for t in ((0, 0), tuning):
+        capi.set_tuning(*t)
+        try:
+            mod = L.Wasserstein1D(**g["meta"]["ctor"])
+            x = g["x"].to(DEV).requires_grad_(True)
+            y = g["y"].to(DEV).requires_grad_(True)
+            v = mod(x, y, x_pos=g["pos_x"].to(DEV), y_pos=g["pos_y"].to(DEV))
+            v.backward()
+        finally:
+            capi.set_tuning(0, 0)
+        cur = (v.item(), x.grad.clone(), y.grad.clone())
+        if base is None:
+            base = cur
+    assert abs(cur[0] - base[0]) <= 1e-6 * abs(base[0])
+    for a, b in ((cur[1], base[1]), (cur[2], base[2])):
+        assert (a - b).norm().item() <= 1e-4 * b.norm().item()
+
+
+# ------------------------------------------------------------------------------------------
+# the rest of the reference's surface
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("p", [1, 2])
+def test_fixed_grid_metric_path(L, p):
+    g = G.load(f"fixedx65_p{p}")
+    mod = L.Wasserstein1D(p=p, fixed_x=65).to(DEV)
+    with torch.inference_mode():  # metrics.py:146
+        value = mod(g["x"].to(DEV), g["y"].to(DEV))
+        per_item = mod(g["x"].to(DEV), g["y"].to(DEV), dims=1)
+    assert torch.allclose(value.cpu(), g["value"], rtol=1e-5, atol=0)
+    assert per_item.shape == g["per_item"].shape
+    assert torch.allclose(per_item.cpu(), g["per_item"], rtol=1e-5, atol=0)
+    # buffer left on the CPU (MixOfLosses keeps a plain list, losses.py:354): still works
+    cpu_buf = L.Wasserstein1D(p=p, fixed_x=65)
+    assert torch.allclose(cpu_buf(g["x"].to(DEV), g["y"].to(DEV)).cpu(), g["value"], rtol=1e-5, atol=0)
+
+
+def test_hinge_gate_and_threshold(L):
+    g = G.load("fixedx65_hinge")
+    mod = L.Wasserstein1D(**g["meta"]["ctor"]).to(DEV)
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = g["y"].to(DEV).requires_grad_(True)
+    v = mod(x, y, **g["meta"]["call"])
+    v.backward()
+    assert torch.allclose(v.cpu(), g["value"], rtol=1e-5, atol=0)
+    for mine, ref in ((x.grad.cpu(), g["grad_x"]), (y.grad.cpu(), g["grad_y"])):
+        assert (mine - ref).norm() <= 2e-3 * ref.norm()
+        assert torch.equal(mine.reshape(30, -1).abs().sum(1) == 0, ref.reshape(30, -1).abs().sum(1) == 0), "hinge gate"
+
+
+@pytest.mark.parametrize("p,limit", [(1, False), (2, True)])
+def test_module_level_w1d_unequal_unsorted_supports(L, p, limit):
+    g = G.load(f"w1d_n37_m90_p{p}")
+    uw = g["u_weights"].to(DEV).requires_grad_(True)
+    vw = g["v_weights"].to(DEV).requires_grad_(True)
+    rows = L.wasserstein_1d(g["u_values"].to(DEV), g["v_values"].to(DEV), uw, vw, p=p, limit_quantile_range=limit)
+    rows.sum().backward()
+    assert torch.allclose(rows.detach().cpu(), g["rows"], rtol=1e-5, atol=1e-8)
+    # random weights: no exact ties, so the gradient is well defined -> compare directly
+    assert (uw.grad.cpu() - g["grad_uw"]).norm() <= 1e-4 * g["grad_uw"].norm()
+    assert (vw.grad.cpu() - g["grad_vw"]).norm() <= 1e-4 * g["grad_vw"].norm()
+    q = L.wasserstein_1d(g["u_values"].to(DEV), g["v_values"].to(DEV), g["u_weights"].to(DEV), g["v_weights"].to(DEV),
+                         p=p, return_quantiles=True)
+    assert len(q) == 5
+    for got, key in zip(q, ("uq", "vq", "qs", "cu", "cv")):
+        assert got.shape == g[key].shape
+        assert torch.allclose(got.cpu(), g[key], rtol=0, atol=3e-7), key
+    u = G.load("w1d_uniform_p2")
+    rows = L.wasserstein_1d(u["u_values"].to(DEV), u["v_values"].to(DEV), p=2)
+    assert torch.allclose(rows.cpu(), u["rows"], rtol=1e-5, atol=1e-8)
+
+
+def test_quantile_function_and_return_quantiles(L):
+    g = G.load("quantile_function")
+    out = L.quantile_function(g["qs"].to(DEV), g["cws"].to(DEV), g["xs"].to(DEV))
+    assert torch.equal(out.cpu(), g["out"])
+    c = G.load("sot512_nocut")
+    mod = L.Wasserstein1D(**c["meta"]["ctor"])
+    q = mod(c["x"].to(DEV), c["y"].to(DEV), x_pos=c["pos_x"].to(DEV), y_pos=c["pos_y"].to(DEV), return_quantiles=True)
+    assert isinstance(q, list) and len(q) == 5
+    for got, key in zip(q, ("uq", "vq", "qs", "cu", "cv")):
+        assert got.shape == c[key].shape, key
+    assert torch.allclose(q[2].cpu(), c["qs"], rtol=0, atol=3e-7)
+    assert torch.allclose(q[3].cpu(), c["cu"], rtol=0, atol=2e-7)
+
+
+def test_analytic_known_answers(L):
+    k = G.load("kat_diracs")
+    x, y = k["x"].to(DEV), k["y"].to(DEV)
+    assert L.Wasserstein1D(p=1, fixed_x=9)(x, y).item() == pytest.approx(0.5, abs=1e-7)
+    assert L.Wasserstein1D(p=2, fixed_x=9)(x, y).item() == pytest.approx(0.25, abs=1e-7)
+    assert L.Wasserstein1D(p=2, fixed_x=9)(x, x).item() == 0.0
+    z = torch.zeros(1, 9, device=DEV)
+    cut = L.Wasserstein1D(p=2, fixed_x=9, dont_normalize=True, limit_quantile_range=True)
+    assert cut(z, y).item() == pytest.approx(k["dead_cut"].item(), abs=1e-7)
+    assert L.Wasserstein1D(p=2, fixed_x=9)(z, y).item() == pytest.approx(k["dead_nocut"].item(), rel=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases: ragged batches, unaligned rows, per-frame supports, empty input, NaN
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_frames", [1, 2, 3, 5, 7, 13])
+@pytest.mark.parametrize("offset", [0, 1])
+def test_ragged_and_unaligned_batches(capi, n_frames, offset):
+    g = G.load("sot512_nocut")
+    F = 257
+    x, y = g["x"].reshape(-1, F), g["y"].reshape(-1, F)
+    pos = g["pos_x"].to(DEV)
+    full_x, full_y = x.to(DEV), y.to(DEV)
+    ref_loss, ref_gu, ref_gv = capi.forward_backward(full_x, full_y, pos, pos, 2.0, capi.SOT_SQUARE)
+    # rows [offset, offset + n_frames): with offset 1 the base pointer is only 4-byte aligned,
+    # and n_frames not a multiple of 4 leaves a ragged tail CTA -> the non-TMA load/store path
+    sx = full_x[offset:offset + n_frames]
+    sy = full_y[offset:offset + n_frames]
+    assert sx.is_contiguous()
+    loss, gu, gv = capi.forward_backward(sx, sy, pos, pos, 2.0, capi.SOT_SQUARE)
+    assert torch.equal(loss, ref_loss[offset:offset + n_frames])
+    assert torch.equal(gu, ref_gu[offset:offset + n_frames]) and torch.equal(gv, ref_gv[offset:offset + n_frames])
+    assert torch.equal(capi.forward(sx, sy, pos, pos, 2.0, capi.SOT_SQUARE), loss)
+
+
+def test_per_frame_supports_match_shared_support(capi, L):
+    g = G.load("sot512_logf_cut")
+    F = 257
+    x, y = g["x"].reshape(-1, F).to(DEV), g["y"].reshape(-1, F).to(DEV)
+    pos = g["pos_x"].to(DEV)
+    flags = capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT
+    a = capi.forward_backward(x, y, pos, pos, 2.0, flags)
+    rep = pos.unsqueeze(0).repeat(x.shape[0], 1).contiguous()
+    b = capi.forward_backward(x, y, rep, rep, 2.0, flags)
+    for s, t in zip(a, b):
+        assert torch.equal(s, t)
+    # module level: 3-D per-frame positions, unsorted along the row (reversed grid + reversed spectra)
+    mod = L.Wasserstein1D(p=2, square_dist=True)
+    x3, y3 = g["x"].to(DEV), g["y"].to(DEV)
+    p3 = pos.expand_as(x3).contiguous()
+    v_sorted = mod(x3, y3, x_pos=p3, y_pos=p3)
+    v_flipped = mod(x3.flip(-1), y3.flip(-1), x_pos=p3.flip(-1).contiguous(), y_pos=p3.flip(-1).contiguous())
+    assert torch.equal(v_sorted, v_flipped)
+
+
+def test_empty_batch_and_zero_spectra(capi, L):
+    pos = torch.linspace(0, 1, 33, device=DEV)
+    e = torch.empty(0, 33, device=DEV)
+    assert capi.forward(e, e, pos, pos, 2.0, 0).shape == (0,)
+    z = torch.zeros(4, 33, device=DEV, requires_grad=True)
+    y = torch.rand(4, 33, device=DEV, requires_grad=True)
+    for cut in (False, True):
+        v = L.Wasserstein1D(p=2, square_dist=True, dont_normalize=cut, limit_quantile_range=cut)(z, y, pos, pos)
+        v.backward()
+        ref = O.sot_loss(torch.zeros(4, 33), y.detach().cpu(), pos.cpu(), pos.cpu(), p=2, square=True, cut_scale=cut,
+                         limit=cut)
+        assert torch.isfinite(v) and v.item() == pytest.approx(ref.item(), rel=1e-5, abs=1e-9)
+        assert torch.isfinite(z.grad).all() and torch.isfinite(y.grad).all()
+
+
+def test_nan_input_poisons_only_its_frame(capi):
+    pos = torch.linspace(0, 1, 65, device=DEV)
+    x = torch.rand(8, 65, device=DEV)
+    y = torch.rand(8, 65, device=DEV)
+    clean = capi.forward(x, y, pos, pos, 2.0, capi.SOT_SQUARE)
+    x[2, 7] = float("nan")
+    loss, gu, gv = capi.forward_backward(x, y, pos, pos, 2.0, capi.SOT_SQUARE)
+    assert torch.isnan(loss[2]) and torch.isnan(gu[2]).all()
+    keep = [0, 1, 3, 4, 5, 6, 7]
+    assert torch.equal(loss[keep], clean[keep]) and torch.isfinite(gu[keep]).all() and torch.isfinite(gv[keep]).all()
+
+
+def test_inputs_are_not_modified_and_wrong_dtype_raises(capi, L):
+    pos = torch.linspace(0, 1, 65, device=DEV)
+    x = torch.rand(8, 65, device=DEV)
+    y = torch.rand(8, 65, device=DEV)
+    x0, y0 = x.clone(), y.clone()
+    capi.forward_backward(x, y, pos, pos, 2.0, capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT)
+    assert torch.equal(x, x0) and torch.equal(y, y0)
+    with pytest.raises(TypeError):
+        L.Wasserstein1D(p=2, fixed_x=65)(x.double(), y.double())
+    half = L.Wasserstein1D(p=2, fixed_x=65).to(DEV)(x.half(), y.half())
+    assert torch.isfinite(half)
+
+
+# ------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json config sizes; the oracle would take minutes here)
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def big_batch():
+    from sot_b200 import synthetic as S
+    x, y = S.sot_batch(1024, 2048, seed=42, device=DEV)  # 16384 frames x 1025 bins
+    return x, y, S.linear_positions(2048).to(DEV)
+
+
+def test_full_size_properties(capi, L, big_batch):
+    x, y, pos = big_batch
+    F = x.shape[-1]
+    xr, yr = x.reshape(-1, F), y.reshape(-1, F)
+    sq = capi.SOT_SQUARE
+    # identical spectra -> exactly zero, in both modes
+    assert capi.forward(xr, xr, pos, pos, 2.0, sq).abs().max().item() == 0.0
+    assert capi.forward(xr, xr, pos, pos, 2.0, sq | capi.SOT_CUT_SCALE | capi.SOT_LIMIT).abs().max().item() == 0.0
+    loss, gu, gv = capi.forward_backward(xr, yr, pos, pos, 2.0, sq)
+    assert torch.isfinite(loss).all() and (loss >= 0).all() and (loss <= 1.0).all()  # supports lie in [0, 1]
+    # symmetry of W_2^2 between two unit-mass measures
+    swapped = capi.forward(yr, xr, pos, pos, 2.0, sq)
+    assert ((loss - swapped).abs() <= 1e-5 * loss.abs() + 1e-9).all()
+    # no-cut mode is invariant to the scale of either spectrum (both are normalised): power-of-two
+    # scalings are exact in floating point, so the result must not change in a single bit
+    assert torch.equal(capi.forward(xr * 4.0, yr * 0.5, pos, pos, 2.0, sq), loss)
+    # ... hence (Euler) <x, dL/dx> = 0 and <y, dL/dy> = 0 per frame, up to the fp32 cancellation
+    # noise of ill-conditioned frames (see the conditioning bound in the fixture test)
+    for gr, sp in ((gu, xr), (gv, yr)):
+        ratio = (gr * sp).sum(1).abs() / ((gr.abs() * sp).sum(1) + 1e-30)
+        assert ratio.median().item() <= 1e-4 and (ratio <= 1e-2).float().mean().item() >= 0.99
+    # cutoff mode: scaling BOTH spectra by the same power of two changes nothing
+    cut = sq | capi.SOT_CUT_SCALE | capi.SOT_LIMIT
+    lc = capi.forward(xr, yr, pos, pos, 2.0, cut)
+    assert torch.equal(capi.forward(xr * 2.0, yr * 2.0, pos, pos, 2.0, cut), lc)
+    # forward-only and fused kernels agree on the loss; the module mean equals the row mean
+    assert torch.equal(capi.forward(xr, yr, pos, pos, 2.0, sq), loss)
+    mod = L.Wasserstein1D(p=2, square_dist=True)
+    assert mod(x, y, x_pos=pos, y_pos=pos).item() == pytest.approx(loss.double().mean().item(), rel=1e-5)
+
+
+def test_full_size_directional_derivative(L, big_batch):
+    """Finite-difference check of the gradient along a random direction, in float32 arithmetic on a
+    large batch (the step is large enough for fp32, small enough for the piecewise-smooth loss)."""
+    x, y, pos = big_batch
+    x, y = x[:256], y[:256]
+    mod = L.Wasserstein1D(p=2, square_dist=True)
+    yv = y.clone().requires_grad_(True)
+    v = mod(x, yv, x_pos=pos, y_pos=pos)
+    v.backward()
+    d = torch.randn_like(y) * y.abs().mean()
+    eps = 1e-2
+    with torch.no_grad():
+        up = mod(x, y + eps * d, x_pos=pos, y_pos=pos)  # weights are magnitudes squared: signs are harmless
+        dn = mod(x, y - eps * d, x_pos=pos, y_pos=pos)
+    fd = (up.double() - dn.double()).item() / (2 * eps)
+    an = (yv.grad.double() * d.double()).sum().item()
+    assert abs(fd - an) <= 0.1 * abs(an) + 1e-6, (fd, an)
+
+
+def test_host_buffer_entry_point_matches_device_path(capi):
+    g = G.load("sot2048_cut")
+    F = 1025
+    x = g["x"].reshape(-1, F).repeat(5, 1)[:37].contiguous().pin_memory()
+    y = g["y"].reshape(-1, F).repeat(5, 1)[:37].contiguous().pin_memory()
+    pos = g["pos_x"].contiguous()
+    flags = capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT
+    up = torch.rand(37)
+    loss, gu, gv = capi.loss_grad_host(x, y, pos, pos, 2.0, flags, upstream=up)
+    d = capi.forward_backward(x.to(DEV), y.to(DEV), pos.to(DEV), pos.to(DEV), 2.0, flags, upstream=up.to(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(loss, d[0].cpu()) and torch.equal(gu, d[1].cpu()) and torch.equal(gv, d[2].cpu())

@@ -69,25 +69,31 @@ def test_unequal_supports():
 
 @pytest.mark.parametrize("cut", [True, False])
 def test_end_to_end_model_vs_stable_autograd(cut):
-    """From magnitudes: the model's fp64-accumulated masses/CDFs make it (nearly always) land on
-    the same fp32 CDFs as the CPU reference, so loss and gradients agree with the stable-sort
-    autograd oracle to rounding."""
+    """From magnitudes.  The model's fp64-accumulated masses/CDFs often land on exactly the
+    reference's fp32 CDFs; on those frames the loss agrees to rounding and the gradient is at
+    least as close to the fp64 continuation of the same CDFs as the reference's own fp32
+    autograd is (the gradient is ill-conditioned in fp32: SURVEY.md App. B)."""
     x, y = _frames(512, 32, seed=456)
     pos = S.linear_positions(512)
-    rows, gx, gy = O.sot_loss_and_grads(torch.from_numpy(x), torch.from_numpy(y), pos, pos,
-                                        upstream=torch.ones(x.shape[0]), p=2, square=True,
-                                        cut_scale=cut, limit=cut, stable=True)
-    uq, vq, qs, cu_ref, cv_ref, _, _ = O.sot_quantiles(torch.from_numpy(x), torch.from_numpy(y),
-                                                     pos, pos, square=True, cut_scale=cut,
-                                                     stable=True)
+    tx, ty = torch.from_numpy(x), torch.from_numpy(y)
+    rows, gx, gy = O.sot_loss_and_grads(tx, ty, pos, pos, upstream=torch.ones(x.shape[0]), p=2,
+                                        square=True, cut_scale=cut, limit=cut, stable=True)
+    _, _, _, cu_ref, cv_ref, _, _ = O.sot_quantiles(tx, ty, pos, pos, square=True, cut_scale=cut,
+                                                    stable=True)
     same_cdf = 0
     for r in range(x.shape[0]):
         loss, mgx, mgy, cu, cv, _, _ = KM.frame_loss_and_grads(x[r], y[r], pos.numpy(), pos.numpy(),
                                                               2, True, cut, cut, 32, 17)
-        if np.array_equal(cu, cu_ref[r].numpy()) and np.array_equal(cv, cv_ref[r].numpy()):
-            same_cdf += 1
-            assert abs(loss - rows[r].item()) <= 2e-6 * abs(rows[r].item())
-            ngx, ngy = gx[r].numpy(), gy[r].numpy()
-            assert np.linalg.norm(mgx - ngx) <= 2e-5 * np.linalg.norm(ngx)
-            assert np.linalg.norm(mgy - ngy) <= 2e-5 * np.linalg.norm(ngy)
+        if not (np.array_equal(cu, cu_ref[r].numpy()) and np.array_equal(cv, cv_ref[r].numpy())):
+            continue
+        same_cdf += 1
+        Ma, Mb = KM.normalise(x[r], y[r], True, cut)[2:4]
+        tl, tgx, tgy = O.fp64_chain_from_cdfs(x[r], y[r], cu, cv, pos.numpy(), pos.numpy(), Ma, Mb,
+                                              2, True, cut, cut)
+        assert abs(loss - rows[r].item()) <= 2e-6 * abs(rows[r].item())
+        assert abs(loss - tl) <= 2e-6 * abs(tl)
+        for mine, ref32, truth in ((mgx, gx[r].numpy(), tgx), (mgy, gy[r].numpy(), tgy)):
+            e_mine = np.linalg.norm(mine - truth) / np.linalg.norm(truth)
+            e_ref = np.linalg.norm(ref32 - truth) / np.linalg.norm(truth)
+            assert e_mine <= max(2e-6, 1.5 * e_ref), (r, e_mine, e_ref)
     assert same_cdf >= x.shape[0] // 4, f"only {same_cdf} frames reproduced the reference CDFs"
