@@ -101,8 +101,8 @@ int cuda_fail(cudaError_t e, const char* what) {
     return static_cast<int>(e);
 }
 
-int smem_need(const Config& c, int n, int m, bool with_grad, bool su, bool sv) {
-    return sot::smem_plan(c.fpc, n, m, c.tpf, with_grad, su, sv).total;
+int smem_need(const Config& c, int n, int m, bool /*with_grad*/, bool su, bool sv) {
+    return sot::smem_plan(c.fpc, n, m, c.tpf, su && sv).total;
 }
 
 const Config* pick_config(int n, int m, bool with_grad, bool su, bool sv) {

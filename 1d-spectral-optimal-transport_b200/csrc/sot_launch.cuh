@@ -14,15 +14,30 @@ struct LaunchRequest {
 template <int TPF, int E, int FPC, int PMODE, int OUT, int MODE>
 cudaError_t launch_one(const FrameArgs& a, cudaStream_t stream) {
     auto kernel = sot_frames_kernel<TPF, E, FPC, PMODE, OUT, MODE>;
-    const SmemPlan plan = smem_plan(FPC, a.n, a.m, TPF, OUT == OUT_GRAD, a.pos_u_stride == 0, a.pos_v_stride == 0);
-    static int configured_bytes = -1;  // per instantiation; grows monotonically
-    if (plan.total > configured_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total);
+    const SmemPlan plan = smem_plan(FPC, a.n, a.m, TPF, a.pos_u_stride == 0 && a.pos_v_stride == 0);
+    // per instantiation (and device): opt-in shared memory size and the persistent grid size
+    static int configured_bytes = -1, cached_bytes = -1, cached_grid = 0, cached_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (plan.total > configured_bytes || dev != cached_dev) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total);
         if (e != cudaSuccess) return e;
         configured_bytes = plan.total;
     }
-    const long long ctas = (a.n_frames + FPC - 1) / FPC;
-    kernel<<<static_cast<unsigned>(ctas), FPC * TPF, plan.total, stream>>>(a);
+    if (plan.total != cached_bytes || dev != cached_dev) {
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, FPC * TPF, plan.total);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        cached_grid = (per_sm < 1 ? 1 : per_sm) * sms;  // persistent: every CTA slot of the chip, once
+        cached_bytes = plan.total;
+        cached_dev = dev;
+    }
+    const long long quads = (a.n_frames + FPC - 1) / FPC;
+    const unsigned grid = static_cast<unsigned>(quads < cached_grid ? quads : cached_grid);
+    kernel<<<grid, FPC * TPF, plan.total, stream>>>(a);
     return cudaGetLastError();
 }
 
