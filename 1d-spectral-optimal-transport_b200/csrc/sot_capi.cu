@@ -11,13 +11,15 @@
 #include "../../include/sot_b200.h"
 #include "sot_launch.cuh"
 
-SOT_DECLARE_CONFIG(32, 9, 4)
-SOT_DECLARE_CONFIG(32, 33, 4)
-SOT_DECLARE_CONFIG(64, 17, 4)
-SOT_DECLARE_CONFIG(128, 9, 4)
-SOT_DECLARE_CONFIG(128, 17, 4)
-SOT_DECLARE_CONFIG(128, 33, 1)
-SOT_DECLARE_CONFIG(256, 33, 1)
+SOT_DECLARE_CONFIG(32, 9, 296)
+SOT_DECLARE_CONFIG(64, 9, 584)
+SOT_DECLARE_CONFIG(128, 9, 1032)
+SOT_DECLARE_CONFIG(64, 17, 1032)
+SOT_DECLARE_CONFIG(32, 33, 1064)
+SOT_DECLARE_CONFIG(128, 9, 1160)
+SOT_DECLARE_CONFIG(128, 17, 2184)
+SOT_DECLARE_CONFIG(256, 17, 4360)
+SOT_DECLARE_CONFIG(256, 33, 8456)
 
 namespace sot {
 // ------------------------------------------------------------------------------------------
@@ -68,22 +70,24 @@ namespace {
 
 using LaunchFn = cudaError_t (*)(const sot::LaunchRequest&, cudaStream_t);
 struct Config {
-    int tpf, e, fpc;
+    int tpf, e, rs;
     LaunchFn fn;
+    int max_bins() const { return tpf * e < rs - 7 ? tpf * e : rs - 7; }
 };
-// Ordered by preference for a given row length: the first entry whose capacity (tpf * e) and
-// shared-memory footprint fit is used.  Chosen from measurements on B200 (profiles/).
+// Ordered by preference for a given row length: the first entry that holds the row is used
+// (choices from measurements on B200, profiles/).  Shared memory per CTA = (4 or 6) * 4 * rs bytes.
 const Config kConfigs[] = {
-    {32, 9, 4, sot_launch_32_9_4},      // <= 288 bins   (n_fft 512: 257)
-    {128, 9, 4, sot_launch_128_9_4},    // <= 1152 bins  (n_fft 2048: 1025)
-    {64, 17, 4, sot_launch_64_17_4},    // <= 1088 bins  alternative shape for 1025
-    {32, 33, 4, sot_launch_32_33_4},    // <= 1056 bins  alternative shape for 1025
-    {128, 17, 4, sot_launch_128_17_4},  // <= 2176 bins  (n_fft 4096)
-    {128, 33, 1, sot_launch_128_33_1},  // <= 4224 bins  (n_fft 8192), one frame per CTA
-    {256, 33, 1, sot_launch_256_33_1},  // <= 8448 bins  (n_fft 16384)
+    {32, 9, 296, sot_launch_32_9_296},        // <= 288 bins   (n_fft 512: 257)
+    {64, 9, 584, sot_launch_64_9_584},        // <= 576 bins   (n_fft 1024: 513)
+    {128, 9, 1032, sot_launch_128_9_1032},    // <= 1025 bins  (n_fft 2048: 1025)
+    {64, 17, 1032, sot_launch_64_17_1032},    //               alternative shapes for 1025 (tuning)
+    {32, 33, 1064, sot_launch_32_33_1064},
+    {128, 9, 1160, sot_launch_128_9_1160},    // <= 1152 bins
+    {128, 17, 2184, sot_launch_128_17_2184},  // <= 2176 bins  (n_fft 4096: 2049)
+    {256, 17, 4360, sot_launch_256_17_4360},  // <= 4352 bins  (n_fft 8192: 4097)
+    {256, 33, 8456, sot_launch_256_33_8456},  // <= 8448 bins  (n_fft 16384: 8193)
 };
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
-constexpr int kMaxSmem = 227 * 1024;
 
 thread_local char g_error[512] = "";
 std::atomic<long long> g_launches{0};
@@ -101,24 +105,17 @@ int cuda_fail(cudaError_t e, const char* what) {
     return static_cast<int>(e);
 }
 
-int smem_need(const Config& c, int n, int m, bool /*with_grad*/, bool su, bool sv) {
-    return sot::smem_plan(c.fpc, n, m, c.tpf, su && sv).total;
-}
-
-const Config* pick_config(int n, int m, bool with_grad, bool su, bool sv) {
+const Config* pick_config(int n, int m) {
     const int need = n > m ? n : m;
     const int tt = g_tune_tpf.load(), te = g_tune_e.load();
     if (tt != 0) {
         for (int i = 0; i < kNumConfigs; ++i) {
             const Config& c = kConfigs[i];
-            if (c.tpf == tt && c.e == te && c.tpf * c.e >= need && smem_need(c, n, m, with_grad, su, sv) <= kMaxSmem)
-                return &c;
+            if (c.tpf == tt && c.e == te && c.max_bins() >= need) return &c;
         }
     }
-    for (int i = 0; i < kNumConfigs; ++i) {
-        const Config& c = kConfigs[i];
-        if (c.tpf * c.e >= need && smem_need(c, n, m, with_grad, su, sv) <= kMaxSmem) return &c;
-    }
+    for (int i = 0; i < kNumConfigs; ++i)
+        if (kConfigs[i].max_bins() >= need) return &kConfigs[i];
     return nullptr;
 }
 
@@ -158,11 +155,10 @@ sot::FrameArgs base_args(const sot_problem* p) {
 
 int launch(const sot_problem* p, sot::LaunchRequest& r, void* stream) {
     if (p->n_frames == 0) return SOT_OK;
-    const bool with_grad = r.out == sot::OUT_GRAD;
-    const Config* c = pick_config(p->n_u, p->n_v, with_grad, p->pos_u_stride == 0, p->pos_v_stride == 0);
+    const Config* c = pick_config(p->n_u, p->n_v);
     if (c == nullptr)
-        return fail(SOT_ETOOBIG, "rows of %d / %d bins do not fit any kernel configuration (shared memory)", p->n_u,
-                    p->n_v);
+        return fail(SOT_ETOOBIG, "rows of %d / %d bins exceed the largest kernel configuration (%d bins)", p->n_u,
+                    p->n_v, sot_max_bins(1, 1));
     cudaError_t e = c->fn(r, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "sot_frames_kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -192,21 +188,10 @@ int sot_set_tuning(int32_t tpf, int32_t e) {
     return fail(SOT_EINVAL, "no kernel configuration with %d threads per frame and %d bins per thread", tpf, e);
 }
 
-int sot_max_bins(int32_t with_grad, int32_t shared_positions) {
+int sot_max_bins(int32_t /*with_grad*/, int32_t /*shared_positions*/) {
     int best = 0;
-    for (int i = 0; i < kNumConfigs; ++i) {
-        const Config& c = kConfigs[i];
-        int lo = 1, hi = c.tpf * c.e;
-        while (lo < hi) {  // largest n (= m) whose footprint fits
-            const int mid = (lo + hi + 1) / 2;
-            if (smem_need(c, mid, mid, with_grad != 0, shared_positions != 0, shared_positions != 0) <= kMaxSmem)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        if (smem_need(c, lo, lo, with_grad != 0, shared_positions != 0, shared_positions != 0) <= kMaxSmem && lo > best)
-            best = lo;
-    }
+    for (int i = 0; i < kNumConfigs; ++i)
+        if (kConfigs[i].max_bins() > best) best = kConfigs[i].max_bins();
     return best;
 }
 

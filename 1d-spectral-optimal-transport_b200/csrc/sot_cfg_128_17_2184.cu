@@ -1,0 +1,3 @@
+// Kernel instantiations: 128 threads per frame, 17 bins per thread, shared-memory rows of 2184 floats.
+#include "sot_launch.cuh"
+SOT_DEFINE_CONFIG(128, 17, 2184)

@@ -1,0 +1,3 @@
+// Kernel instantiations: 256 threads per frame, 17 bins per thread, shared-memory rows of 4360 floats.
+#include "sot_launch.cuh"
+SOT_DEFINE_CONFIG(256, 17, 4360)

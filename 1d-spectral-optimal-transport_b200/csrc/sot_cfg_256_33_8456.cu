@@ -1,0 +1,3 @@
+// Kernel instantiations: 256 threads per frame, 33 bins per thread, shared-memory rows of 8456 floats.
+#include "sot_launch.cuh"
+SOT_DEFINE_CONFIG(256, 33, 8456)

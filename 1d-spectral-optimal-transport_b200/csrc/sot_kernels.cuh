@@ -1,6 +1,5 @@
-// SOT frame kernel (v2): per-frame 1-D Wasserstein (W_p^p) between two spectra, forward and
-// fused forward+backward.  Persistent CTAs; a frame is processed by a group of TPF threads, FPC
-// frames ("a quad") per CTA iteration.
+// SOT frame kernel (v3): per-frame 1-D Wasserstein (W_p^p) between two spectra, forward and
+// fused forward+backward.  ONE FRAME PER CTA of TPF threads, persistent grid, many CTAs per SM.
 //
 // Reference semantics reproduced (file:line into /root/reference):
 //   losses.py:172-184  square, mass, safe_divide (cut mode divides the prediction by the
@@ -9,28 +8,26 @@
 //   losses.py:295      sort(cat(cu, cv))                  -> merge-path partition + sequential walk
 //   losses.py:214-220  searchsorted-left + clamp + gather -> running co-ranks of the walk
 //   losses.py:301-313  sum_k dq_k * |uq_k - vq_k|^p, strict `qs > 1` mask
-//   autograd of all of the above          -> dL/dCDF written in place, suffix
-//                                                           scans, normalisation chain rule, 2x
+//   autograd of all of the above          -> dL/dCDF array, suffix scans,
+//                                                           normalisation chain rule, 2x
 //
-// Shared memory per CTA (n = bins of u, m = bins of v, S = n + m + 2):
-//   LAND  : 4*FPC*(n+m) B   landing zone of the TMA bulk loads: FPC raw rows of u, then of v.
-//                           Read once into registers; the NEXT quad's load is issued as soon as
-//                           every thread has done so, i.e. it overlaps the whole computation.
-//   PAIRS : 8*FPC*S B       per frame S float2 "pairs" (cdf value, support position):
-//                           A[0..n] for u then B[0..m] for v, entries [n] / [m] = (+inf, last pos)
-//                           (sentinel + the reference's index clamp, losses.py:220).  One LDS.64
-//                           per merged slot.  At the end of an iteration of the gradient kernel the
-//                           region is reused to stage the output rows.
-//   (G)   : 4*FPC*S B       gradient kernel only, ALIASED onto LAND once the raw rows are in registers:
-//                           dL/dCDF of every entry, same index space as PAIRS.  (Writing it into the .y
-//                           of the consumed pair instead would race: a thread may load its end-of-range
-//                           head pair after the neighbour that owns it has already consumed it.)  The
-//                           price: the gradient kernel prefetches the next quad only after stage 4.
-//   POS   : 4*S B           support positions (once per CTA when shared, else per frame)
-//   small : scan scratch, first-slot mailbox + carry per thread, mbarrier
-// Thread t of a group owns the E consecutive bins [t*E, t*E+E) of both rows ("blocked"); E is
-// odd so every blocked access of a warp is bank-conflict free and no 16-byte alignment of the
-// 4*n-byte rows is ever needed (n = 1025 / 257: rows are only 4-byte aligned).
+// Shared memory: rows of RS floats at COMPILE-TIME offsets, so that for a CDF entry at shared
+// address a its support position is at a + POS_OFF and its dL/dCDF at a + G_OFF (immediates):
+//   row 0 / 1 : CDF of u / v, entry [n] / [m] = +inf sentinel
+//   row 2 / 3 : support positions of u / v, entry [n] / [m] repeats the last one (the
+//               reference's clamp of the searchsorted index, losses.py:220); written once per
+//               CTA when the support is shared by all frames
+//   row 4 / 5 : (gradient kernel) dL/dCDF of u / v
+//   then      : scan scratch, first-slot mailbox + carry per thread, mbarrier
+// The raw rows of a frame arrive by TMA bulk copy (`cp.async.bulk`, SASS UBLKCP).  A 4*n-byte row
+// is only 4-byte aligned (n = 1025 / 257), the bulk unit is 16 bytes: the copy therefore fetches
+// the 16-byte aligned WINDOW around the row and the kernel skips the `lead` bytes in front.  The
+// landing zone is rows 0/1 (forward: each thread has its bins in registers before the CDF is
+// written in place) or rows 4/5 (gradient: free until the walk; the next frame is prefetched into
+// them as soon as stage 4 has consumed dL/dCDF).  Gradient rows leave the same way: staged in rows
+// 0/1 at the row's own 16-byte phase, bulk store of the aligned middle, <= 3 scalar stores per edge.
+// Thread t owns the E consecutive bins [t*E, t*E+E) of both rows ("blocked"); E is odd so every
+// blocked access of a warp is bank-conflict free.
 #pragma once
 #include "sot_device.cuh"
 
@@ -85,33 +82,21 @@ struct FrameArgs {
 SOT_DEVINL float f_inf() { return __int_as_float(0x7f800000); }
 SOT_DEVINL float f_nan() { return __int_as_float(0x7fc00000); }
 
-// Shared-memory carve-up, shared between host (size) and device (offsets), all in bytes.
-struct SmemPlan {
-    int land, pairs, pos, scratch, mailbox, carry, mbar, total;
+// ---- compile-time shared-memory layout ---------------------------------------------------------
+template <int TPF, int RS, int OUT>
+struct Layout {
+    static constexpr uint32_t ROW = 4u * RS;
+    static constexpr uint32_t A = 0, B = ROW;     // CDF rows (also forward landing zone / output staging)
+    static constexpr uint32_t POS_OFF = 2 * ROW;  // cdf address -> position address
+    static constexpr uint32_t G_OFF = 4 * ROW;    // cdf address -> dL/dCDF address
+    static constexpr uint32_t ROWS = (OUT == OUT_GRAD) ? 6 : 4;
+    static constexpr uint32_t SCRATCH = ROWS * ROW;               // 8 doubles per warp
+    static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per thread + end marker
+    static constexpr uint32_t CARRY = MBOX + 8u * (TPF + 1);
+    static constexpr uint32_t MBAR = (CARRY + 4u * TPF + 15u) & ~15u;
+    static constexpr uint32_t TOTAL = MBAR + 16u;
+    static constexpr int MAX_BINS = RS - 7;  // sentinel + up to 3 floats of lead + rounding of the bulk window
 };
-__host__ __device__ inline SmemPlan smem_plan(int FPC, int n, int m, int tpf, bool pos_shared) {
-    SmemPlan s;
-    int off = 0;
-    s.land = off;
-    off += 4 * FPC * (n + m + 2);  // raw rows, later dL/dCDF (n + m + 2 entries per frame)
-    off = (off + 15) & ~15;
-    s.pairs = off;
-    off += 8 * FPC * (n + m + 2);
-    s.pos = off;
-    off += 4 * (n + m + 2) * (pos_shared ? 1 : FPC);
-    off = (off + 15) & ~15;
-    s.scratch = off;
-    off += 8 * FPC * 16 * (tpf / 32);  // per group: 8 collective slots x warps (+ spare)
-    s.mailbox = off;
-    off += 8 * FPC * (tpf + 1);  // (first q, first m*d) per thread + one end marker
-    s.carry = off;
-    off += 4 * FPC * tpf;
-    off = (off + 15) & ~15;
-    s.mbar = off;
-    off += 16;
-    s.total = off;
-    return s;
-}
 
 // ---- raw shared-memory access by 32-bit shared address (exact instructions, no generic ptrs) ---
 SOT_DEVINL float lds32(uint32_t a) {
@@ -119,16 +104,44 @@ SOT_DEVINL float lds32(uint32_t a) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
+template <uint32_t OFF>
+SOT_DEVINL float lds32o(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+SOT_DEVINL void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+template <uint32_t OFF>
+SOT_DEVINL void sts32o(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(a), "f"(v), "n"(OFF) : "memory");
+}
 SOT_DEVINL void lds64(uint32_t a, float& x, float& y) {
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a));
 }
-SOT_DEVINL void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 SOT_DEVINL void sts64(uint32_t a, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
 // One merge step's advance: the consumed side (v if b < a, else u: u first on equal values, the
-// stable order of `cat(cu, cv)`) loads its next pair and moves its address; both halves are
-// predicated -- no branch, no select.  `consumed` returns the address of the pair that was taken.
+// stable order of `cat(cu, cv)`) loads its next CDF entry and that entry's position and moves its
+// address; everything is predicated -- no branch, no select.  POS4 = POS_OFF + 4.
+template <uint32_t POS4>
+SOT_DEVINL void advance_fwd(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB) {
+    asm volatile(
+        "{\n"
+        ".reg .pred tv;\n"
+        "setp.lt.f32 tv, %2, %0;\n"
+        "@tv  ld.shared.f32 %2, [%5+4];\n"
+        "@tv  ld.shared.f32 %3, [%5+%6];\n"
+        "@!tv ld.shared.f32 %0, [%4+4];\n"
+        "@!tv ld.shared.f32 %1, [%4+%6];\n"
+        "@tv  add.u32 %5, %5, 4;\n"
+        "@!tv add.u32 %4, %4, 4;\n"
+        "}"
+        : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB)
+        : "n"(POS4));
+}
+// same, and returns the address of the CDF entry that was consumed
+template <uint32_t POS4>
 SOT_DEVINL void advance(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB,
                         uint32_t& consumed) {
     asm volatile(
@@ -136,24 +149,15 @@ SOT_DEVINL void advance(float& a, float& pa, float& b, float& pb, uint32_t& adrA
         ".reg .pred tv;\n"
         "setp.lt.f32 tv, %2, %0;\n"
         "selp.u32 %6, %5, %4, tv;\n"
-        "@tv  ld.shared.v2.f32 {%2, %3}, [%5+8];\n"
-        "@!tv ld.shared.v2.f32 {%0, %1}, [%4+8];\n"
-        "@tv  add.u32 %5, %5, 8;\n"
-        "@!tv add.u32 %4, %4, 8;\n"
+        "@tv  ld.shared.f32 %2, [%5+4];\n"
+        "@tv  ld.shared.f32 %3, [%5+%7];\n"
+        "@!tv ld.shared.f32 %0, [%4+4];\n"
+        "@!tv ld.shared.f32 %1, [%4+%7];\n"
+        "@tv  add.u32 %5, %5, 4;\n"
+        "@!tv add.u32 %4, %4, 4;\n"
         "}"
-        : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB), "=r"(consumed));
-}
-SOT_DEVINL void advance_fwd(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB) {
-    asm volatile(
-        "{\n"
-        ".reg .pred tv;\n"
-        "setp.lt.f32 tv, %2, %0;\n"
-        "@tv  ld.shared.v2.f32 {%2, %3}, [%5+8];\n"
-        "@!tv ld.shared.v2.f32 {%0, %1}, [%4+8];\n"
-        "@tv  add.u32 %5, %5, 8;\n"
-        "@!tv add.u32 %4, %4, 8;\n"
-        "}"
-        : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB));
+        : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB), "=r"(consumed)
+        : "n"(POS4));
 }
 
 // fp64 reciprocal of a positive float >= 1e-7: hardware approximation + two Newton steps
@@ -165,9 +169,19 @@ SOT_DEVINL double recip_f64(float x) {
     return r;
 }
 
-// Exclusive scan (prefix; suffix when REVERSE) of one fp64 value over the TPF threads of a group.
+template <int TPF>
+SOT_DEVINL void cta_sync() {
+    if constexpr (TPF == 32) {
+        __syncwarp();
+    } else {
+        __syncthreads();
+    }
+}
+
+// Exclusive scan (prefix; suffix when REVERSE) of one fp64 value over the TPF threads of the CTA.
+// Contains one CTA barrier when the CTA has more than one warp.
 template <int TPF, bool REVERSE>
-SOT_DEVINL void group_scan1(double& a, double& total, double* slot, int tid, int g) {
+SOT_DEVINL void cta_scan1(double& a, double& total, double* slot, int tid) {
     constexpr int NW = TPF / 32;
     const int lane = tid & 31, w = tid >> 5;
     double ia = a;
@@ -185,7 +199,7 @@ SOT_DEVINL void group_scan1(double& a, double& total, double* slot, int tid, int
         total = wa;
     } else {
         if (lane == 0) slot[w] = wa;
-        group_sync<TPF>(g);
+        __syncthreads();
         double pa = 0.0, ta = 0.0;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
@@ -199,13 +213,14 @@ SOT_DEVINL void group_scan1(double& a, double& total, double* slot, int tid, int
     }
 }
 
-// Register budget per thread -> resident CTAs per SM requested from ptxas.
-constexpr int reg_budget(int e, int out) {
-    return out == OUT_GRAD ? (e <= 9 ? 64 : (e <= 17 ? 96 : 128)) : (e <= 9 ? 64 : (e <= 17 ? 80 : 128));
-}
-constexpr int min_ctas(int threads, int e, int out) {
-    const int c = 65536 / (threads * reg_budget(e, out));
-    return c < 1 ? 1 : (c > 16 ? 16 : c);
+// Resident CTAs per SM requested from ptxas: as many as the shared-memory footprint allows,
+// within a sane register budget (forward >= 40, gradient >= 64 registers per thread).
+constexpr int min_ctas(int tpf, int e, int smem_bytes, int out) {
+    const int by_smem = (227 * 1024) / (smem_bytes + 1024);
+    const int regs = out == OUT_GRAD ? (e <= 9 ? 64 : (e <= 17 ? 96 : 168)) : (e <= 9 ? 40 : (e <= 17 ? 64 : 128));
+    const int by_regs = 65536 / (tpf * regs);
+    const int c = by_smem < by_regs ? by_smem : by_regs;
+    return c < 1 ? 1 : (c > 32 ? 32 : c);
 }
 __host__ __device__ constexpr int ilog2_ceil(int x) {
     int b = 0;
@@ -213,181 +228,158 @@ __host__ __device__ constexpr int ilog2_ceil(int x) {
     return b;
 }
 
-template <int TPF, int E, int FPC, int PMODE, int OUT, int MODE>
-__global__ void __launch_bounds__(FPC* TPF, min_ctas(FPC* TPF, E, OUT)) sot_frames_kernel(const FrameArgs args) {
+// 16-byte aligned window around row `f` of a [frames, width] fp32 array
+struct Window {
+    const char* src;  // aligned start
+    uint32_t lead;    // bytes between the window start and the row start (0, 4, 8, 12)
+    uint32_t bytes;   // window size, multiple of 16
+    bool bulk;        // the window lies inside the array: safe to fetch with a bulk copy
+};
+SOT_DEVINL Window row_window(const float* base, long long f, int width, long long frames) {
+    const uintptr_t row = reinterpret_cast<uintptr_t>(base + f * width);
+    const uintptr_t start = row & ~static_cast<uintptr_t>(15);
+    Window w;
+    w.src = reinterpret_cast<const char*>(start);
+    w.lead = static_cast<uint32_t>(row - start);
+    w.bytes = (w.lead + 4u * width + 15u) & ~15u;
+    w.bulk = start >= reinterpret_cast<uintptr_t>(base) &&
+             start + w.bytes <= reinterpret_cast<uintptr_t>(base + frames * width);
+    return w;
+}
+
+template <int TPF, int E, int RS, int PMODE, int OUT, int MODE>
+__global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TOTAL, OUT))
+    sot_frame_kernel(const FrameArgs args) {
+    using LY = Layout<TPF, RS, OUT>;
     constexpr bool WITH_GRAD = (OUT == OUT_GRAD);
-    constexpr int NT = FPC * TPF;
     constexpr int NW = TPF / 32;
-    constexpr int SEARCH_TOP = 1 << (ilog2_ceil(TPF * E + 1) - 1);  // largest power of two <= capacity
+    constexpr int SEARCH_TOP = 1 << (ilog2_ceil(TPF * E + 1) - 1);
     constexpr uint32_t NO_FIX = 0xffffffffu;
+    constexpr uint32_t POS4 = LY::POS_OFF + 4;
+    constexpr uint32_t LAND = WITH_GRAD ? LY::G_OFF : LY::A;  // landing zone rows (u, then v at + ROW)
     extern __shared__ __align__(128) unsigned char smem[];
 
-    const int n = args.n, m = args.m, K = n + m, S = n + m + 2;
+    const int n = args.n, m = args.m, K = n + m;
     const bool square = args.flags & FLAG_SQUARE;
     const bool cut_scale = args.flags & FLAG_CUT_SCALE;
     const bool pos_shared = (args.pos_u_stride == 0) && (args.pos_v_stride == 0);
     // contributions with q above `thr` are dropped: the strict `qs > 1` mask (losses.py:307) when
     // limiting, otherwise nothing a real slot can reach
     const float thr = (args.flags & FLAG_LIMIT) ? 1.0f : FLT_BIG;
-    const SmemPlan plan = smem_plan(FPC, n, m, TPF, pos_shared);
     const uint32_t sb = smem_u32(smem);
+    const uint32_t A0 = sb + LY::A, B0 = sb + LY::B;
 
-    const int g = threadIdx.x / TPF, tid = threadIdx.x % TPF;
+    const int tid = threadIdx.x;
     const int e0 = tid * E;
-    float* const land = reinterpret_cast<float*>(smem + plan.land);
-    float* const posf = reinterpret_cast<float*>(smem + plan.pos);
-    float* const outf = reinterpret_cast<float*>(smem + plan.pairs);  // output staging (end of iteration)
-    double* const scratch = reinterpret_cast<double*>(smem + plan.scratch) + g * 16 * NW;
-    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem + plan.mbar);
-    const uint32_t landU = sb + plan.land + 4u * (g * n + e0);            // my first raw u bin
-    const uint32_t landV = sb + plan.land + 4u * (FPC * n + g * m + e0);  // my first raw v bin
-    const uint32_t PA0 = sb + plan.pairs + 8u * (g * S);                  // pair A[0] of my frame
-    const uint32_t PB0 = PA0 + 8u * (n + 1);                              // pair B[0]
-    const uint32_t posU = sb + plan.pos + 4u * ((pos_shared ? 0 : g * S) + e0);
-    const uint32_t posV = posU + 4u * (n + 1);
-    const uint32_t mbox = sb + plan.mailbox + 8u * (g * (TPF + 1));
-    const uint32_t carry = sb + plan.carry + 4u * (g * TPF);
+    float* const fsm = reinterpret_cast<float*>(smem);
+    double* const scratch = reinterpret_cast<double*>(smem + LY::SCRATCH);
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem + LY::MBAR);
+    const uint32_t mbox = sb + LY::MBOX, carry = sb + LY::CARRY;
     const bool in_u = e0 + E <= n, in_v = e0 + E <= m;  // all of my E bins exist (no guards needed)
 
     // L consecutive merged slots per thread.  L is ODD on purpose: for a balanced merge thread t starts
-    // near pair L*t/2 of each row, and an even L would put the 16 lanes of a half-warp on only two
-    // distinct bank pairs (8-way conflicts on every LDS.64 of the walk, measured); odd L spreads them.
+    // near entry L*t/2 of each row, and an even L would put the lanes of a warp on few distinct banks
+    // (measured: 8-way conflicts on every load of the walk); odd L spreads them.
     const int L = ((K + TPF - 1) / TPF) | 1;
     const int k0 = min(tid * L, K);
     const int cnt = min(L, K - k0);
-    const uint32_t GOFF = (sb + plan.land + 4u * (g * S)) - (PA0 >> 1);  // pair address -> dL/dCDF address
-    (void)GOFF;
 
-    const long long n_quads = (args.n_frames + FPC - 1) / FPC;
-    const bool rows16 = ((FPC * n) % 4 == 0) && ((FPC * m) % 4 == 0);  // always true for FPC == 4
-    const bool in_aligned = rows16 && ((reinterpret_cast<uintptr_t>(args.u) & 15) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(args.v) & 15) == 0);
-    const bool out_aligned = rows16 && ((reinterpret_cast<uintptr_t>(args.grad_u) & 15) == 0) &&
-                             ((reinterpret_cast<uintptr_t>(args.grad_v) & 15) == 0);
-
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
+        sts64(mbox + 8u * TPF, f_inf(), 0.0f);  // virtual slot K: a new group with m*d = 0
     }
-    if (pos_shared) {  // positions once per CTA; entry [n] / [m] repeats the last one (index clamp)
-        for (int idx = threadIdx.x; idx < S; idx += NT)
-            posf[idx] = idx <= n ? args.pos_u[min(idx, n - 1)] : args.pos_v[min(idx - n - 1, m - 1)];
+    if (pos_shared) {  // positions once per CTA
+        for (int idx = tid; idx <= n; idx += TPF) fsm[2 * RS + idx] = args.pos_u[min(idx, n - 1)];
+        for (int idx = tid; idx <= m; idx += TPF) fsm[3 * RS + idx] = args.pos_v[min(idx, m - 1)];
     }
-    if (tid == 0) sts64(mbox + 8u * TPF, f_inf(), 0.0f);  // virtual slot K: a new group with m*d = 0
     __syncthreads();
 
-    auto issue_load = [&](long long quad) {  // one elected thread
-        const long long f0 = quad * FPC;
-        mbar_expect_tx(mbar, 4u * FPC * static_cast<uint32_t>(n + m));
-        bulk_g2s(land, args.u + f0 * n, 4u * FPC * n, mbar);
-        bulk_g2s(land + FPC * n, args.v + f0 * m, 4u * FPC * m, mbar);
+    auto issue_load = [&](const Window& wu, const Window& wv) {  // one elected thread
+        mbar_expect_tx(mbar, wu.bytes + wv.bytes);
+        bulk_g2s(smem + LAND, wu.src, wu.bytes, mbar);
+        bulk_g2s(smem + LAND + LY::ROW, wv.src, wv.bytes, mbar);
     };
-    auto quad_is_bulk = [&](long long quad) { return in_aligned && (quad + 1) * FPC <= args.n_frames; };
 
-    long long quad = blockIdx.x;
+    long long frame = blockIdx.x;
     uint32_t parity = 0;
-    if (quad < n_quads && quad_is_bulk(quad) && threadIdx.x == 0) issue_load(quad);
+    if (frame < args.n_frames && tid == 0) {
+        const Window wu = row_window(args.u, frame, n, args.n_frames), wv = row_window(args.v, frame, m, args.n_frames);
+        if (wu.bulk && wv.bulk) issue_load(wu, wv);
+    }
 
-    for (; quad < n_quads; quad += gridDim.x) {
-        const long long frame0 = quad * FPC;
-        const long long left = args.n_frames - frame0;
-        const int nfr = left < FPC ? static_cast<int>(left) : FPC;
-        const bool active = g < nfr;
-        const long long frame = frame0 + g;
-
-        // ---- stage 0: the quad's raw rows are (or get) in LAND --------------------------------
-        if (quad_is_bulk(quad)) {
+    for (; frame < args.n_frames; frame += gridDim.x) {
+        // ---- stage 0: the frame's raw rows are (or get) in the landing zone ----------------------
+        const Window wu = row_window(args.u, frame, n, args.n_frames), wv = row_window(args.v, frame, m, args.n_frames);
+        const bool bulk_in = wu.bulk && wv.bulk;
+        uint32_t rawU = sb + LAND + 4u * e0, rawV = sb + LAND + LY::ROW + 4u * e0;  // my first raw bins
+        if (bulk_in) {
             mbar_wait(mbar, parity);
             parity ^= 1;
-        } else {  // ragged last quad or 4-byte aligned base pointers: plain coalesced loads
-            const float* gu = args.u + frame0 * n;
-            const float* gv = args.v + frame0 * m;
-            for (int idx = threadIdx.x; idx < nfr * n; idx += NT) land[idx] = gu[idx];
-            for (int idx = threadIdx.x; idx < nfr * m; idx += NT) land[FPC * n + idx] = gv[idx];
-            __syncthreads();
+            rawU += wu.lead;
+            rawV += wv.lead;
+        } else {  // first / last row of an array whose ends are not 16-byte aligned: plain coalesced loads
+            const float* gu = args.u + frame * n;
+            const float* gv = args.v + frame * m;
+            for (int idx = tid; idx < n; idx += TPF) fsm[LAND / 4 + idx] = gu[idx];
+            for (int idx = tid; idx < m; idx += TPF) fsm[LAND / 4 + RS + idx] = gv[idx];
+            cta_sync<TPF>();
         }
-        if (!pos_shared) {  // per-frame supports: (re)load this quad's rows
-            for (int idx = threadIdx.x; idx < nfr * S; idx += NT) {
-                const int r = idx / S, c = idx - r * S;
-                posf[idx] = c <= n ? args.pos_u[(frame0 + r) * args.pos_u_stride + min(c, n - 1)]
-                                   : args.pos_v[(frame0 + r) * args.pos_v_stride + min(c - n - 1, m - 1)];
-            }
-        }
-
-        // ---- stage 1: blocked read of my E bins of each row (conflict free: E is odd) ---------
-        float xu[E], xv[E];
-        if (in_u) {
-#pragma unroll
-            for (int c = 0; c < E; ++c) xu[c] = lds32(landU + 4 * c);
-        } else {
-#pragma unroll
-            for (int c = 0; c < E; ++c) xu[c] = (e0 + c < n) ? lds32(landU + 4 * c) : 0.0f;
-        }
-        if (in_v) {
-#pragma unroll
-            for (int c = 0; c < E; ++c) xv[c] = lds32(landV + 4 * c);
-        } else {
-#pragma unroll
-            for (int c = 0; c < E; ++c) xv[c] = (e0 + c < m) ? lds32(landV + 4 * c) : 0.0f;
+        if (!pos_shared) {  // per-frame supports
+            const float* gpu = args.pos_u + frame * args.pos_u_stride;
+            const float* gpv = args.pos_v + frame * args.pos_v_stride;
+            for (int idx = tid; idx <= n; idx += TPF) fsm[2 * RS + idx] = gpu[min(idx, n - 1)];
+            for (int idx = tid; idx <= m; idx += TPF) fsm[3 * RS + idx] = gpv[min(idx, m - 1)];
         }
         if constexpr (WITH_GRAD) {
-            // the previous iteration's output store must have finished READING the staging area
-            // (PAIRS region) before stage 2 of this iteration overwrites it
-            if (threadIdx.x == 0) bulk_wait_read_all();
-        }
-        __syncthreads();  // LAND is free again (and, per-frame supports, POS is complete)
-        if constexpr (!WITH_GRAD) {  // (the gradient kernel reuses LAND for dL/dCDF first)
-            const long long next = quad + gridDim.x;
-            if (threadIdx.x == 0 && next < n_quads && quad_is_bulk(next)) issue_load(next);
+            // the previous frame's output store must have finished READING its staging rows (rows 0/1)
+            // before this frame's CDFs are written there
+            if (tid == 0) bulk_wait_read_all();
         }
 
         float acc = 0.0f;    // my part of the frame's loss
         bool finite = true;  // masses (and the scaled totals) are finite numbers
         double inv_u = 1.0, inv_v = 1.0;
         bool u_live = false, v_live = false;  // mass above the safe_divide floor -> carries gradient
-        float og_u[E], og_v[E];               // (WITH_GRAD) finished gradient values of my bins
-        (void)og_u;
-        (void)og_v;
+        float xu[E], xv[E];                   // raw bins (the gradient kernel needs them again at the end)
         (void)inv_v;
         (void)u_live;
         (void)v_live;
 
-        if (active) {
-            // ---- stage 2: masses and CDFs (fp64 accumulation, one rounding to fp32 per entry),
-            //      written as (cdf, position) pairs -------------------------------------------------
-            if constexpr (MODE == MODE_SPECTRA) {
-                double P[E];
+        // ---- stages 1 + 2: blocked read of my E bins (conflict free: E is odd), masses and CDFs
+        //      (fp64 accumulation, one rounding to fp32 per entry) ---------------------------------------
+        if constexpr (MODE == MODE_SPECTRA) {
+            double P[E];
+            double tot_u, tot_v;
+            {
                 double t = 0.0;
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
+                    xu[c] = (in_u || e0 + c < n) ? lds32(rawU + 4 * c) : 0.0f;
                     t += static_cast<double>(square ? xu[c] * xu[c] : xu[c]);
                     P[c] = t;
                 }
-                double off = t, tot_u;
-                group_scan1<TPF, false>(off, tot_u, scratch, tid, g);
+                double off = t;
+                cta_scan1<TPF, false>(off, tot_u, scratch, tid);  // (its barrier also orders raw reads before CDF writes)
                 const float mass_u = static_cast<float>(tot_u);
                 u_live = mass_u > SAFE_EPS;  // utils.py:137: den <= eps -> eps
                 inv_u = recip_f64(u_live ? mass_u : SAFE_EPS);
                 if (args.flags & FLAG_RAW) inv_u = 1.0;
-                if (in_u) {
+                if constexpr (NW == 1) __syncwarp();
 #pragma unroll
-                    for (int c = 0; c < E; ++c)
-                        sts64(PA0 + 8 * (e0 + c), static_cast<float>((off + P[c]) * inv_u), lds32(posU + 4 * c));
-                } else {
-#pragma unroll
-                    for (int c = 0; c < E; ++c)
-                        if (e0 + c < n)
-                            sts64(PA0 + 8 * (e0 + c), static_cast<float>((off + P[c]) * inv_u), lds32(posU + 4 * c));
-                }
-                t = 0.0;
+                for (int c = 0; c < E; ++c)
+                    if (in_u || e0 + c < n) sts32(A0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_u));
+            }
+            {
+                double t = 0.0;
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
+                    xv[c] = (in_v || e0 + c < m) ? lds32(rawV + 4 * c) : 0.0f;
                     t += static_cast<double>(square ? xv[c] * xv[c] : xv[c]);
                     P[c] = t;
                 }
-                double tot_v;
-                off = t;
-                group_scan1<TPF, false>(off, tot_v, scratch + NW, tid, g);
+                double off = t;
+                cta_scan1<TPF, false>(off, tot_v, scratch + NW, tid);
                 const float mass_v = static_cast<float>(tot_v);
                 v_live = mass_v > SAFE_EPS;
                 inv_v = cut_scale ? inv_u : recip_f64(v_live ? mass_v : SAFE_EPS);
@@ -395,328 +387,354 @@ __global__ void __launch_bounds__(FPC* TPF, min_ctas(FPC* TPF, E, OUT)) sot_fram
                     inv_v = 1.0;
                     u_live = v_live = false;
                 }
-                if (in_v) {
+                if constexpr (NW == 1) __syncwarp();
 #pragma unroll
-                    for (int c = 0; c < E; ++c)
-                        sts64(PB0 + 8 * (e0 + c), static_cast<float>((off + P[c]) * inv_v), lds32(posV + 4 * c));
-                } else {
+                for (int c = 0; c < E; ++c)
+                    if (in_v || e0 + c < m) sts32(B0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_v));
+            }
+            // NaN / inf anywhere (or an overflowing cut-mode scale) poisons the frame: the walk is skipped
+            // (its +inf sentinels must stay unique) and NaN is written instead
+            finite = (fabs(tot_u * inv_u) <= static_cast<double>(FLT_BIG)) &&
+                     (fabs(tot_v * inv_v) <= static_cast<double>(FLT_BIG));
+        } else {
 #pragma unroll
-                    for (int c = 0; c < E; ++c)
-                        if (e0 + c < m)
-                            sts64(PB0 + 8 * (e0 + c), static_cast<float>((off + P[c]) * inv_v), lds32(posV + 4 * c));
+            for (int c = 0; c < E; ++c) {
+                xu[c] = (e0 + c < n) ? lds32(rawU + 4 * c) : 0.0f;
+                xv[c] = (e0 + c < m) ? lds32(rawV + 4 * c) : 0.0f;
+            }
+            cta_sync<TPF>();  // the rows are shifted in place by `lead`: all reads before any write
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                if (e0 + c < n) sts32(A0 + 4 * (e0 + c), fminf(xu[c], FLT_BIG));
+                if (e0 + c < m) sts32(B0 + 4 * (e0 + c), fminf(xv[c], FLT_BIG));
+            }
+        }
+        if (tid == 0) {
+            sts32(A0 + 4 * n, f_inf());
+            sts32(B0 + 4 * m, f_inf());
+        }
+        cta_sync<TPF>();
+
+        uint32_t adrA = A0, adrB = B0;
+        float a = 0.0f, pa = 0.0f, b = 0.0f, pb = 0.0f, qprev = 0.0f;
+        int i0 = 0;
+        if (finite) {
+            // ---- stage 3a: merge-path partition (fixed-trip, branch-free bit descent) ---------------
+            // i0 = number of u entries among the first k0 merged slots (u first on equal values):
+            // the largest i in [lo, hi] with A[i-1] <= B[k0-i]
+            {
+                const int lo = max(0, k0 - m), hi = min(k0, n);
+                uint32_t cur = A0 + 4u * lo;  // address of A[i] for the current i
+                const uint32_t hiA = A0 + 4u * hi;
+                const uint32_t sumAB = A0 + B0 + 4u * k0;  // addr(A[i]) + addr(B[k0-i]) is constant
+#pragma unroll
+                for (int step = SEARCH_TOP; step >= 1; step >>= 1) {
+                    const uint32_t cand = cur + 4u * step;
+                    if (cand <= hiA) {
+                        const float av = lds32(cand - 4);      // A[i-1] for the candidate i
+                        const float bv = lds32(sumAB - cand);  // B[k0-i]
+                        if (av <= bv) cur = cand;
+                    }
                 }
-                // NaN / inf anywhere (or an overflowing cut-mode scale) poisons the frame: the walk
-                // is skipped (its +inf sentinels must stay unique) and NaN is written instead
-                finite = (fabs(tot_u * inv_u) <= static_cast<double>(FLT_BIG)) &&
-                         (fabs(tot_v * inv_v) <= static_cast<double>(FLT_BIG));
+                i0 = static_cast<int>((cur - A0) >> 2);
+            }
+            adrA = A0 + 4u * i0;
+            adrB = B0 + 4u * (k0 - i0);
+            a = lds32(adrA);
+            pa = lds32o<LY::POS_OFF>(adrA);
+            b = lds32(adrB);
+            pb = lds32o<LY::POS_OFF>(adrB);
+            if (k0 > 0) {  // else: the zero the reference pads in front of qs (losses.py:301)
+                const float al = i0 > 0 ? lds32(adrA - 4) : -f_inf();
+                const float bl = k0 - i0 > 0 ? lds32(adrB - 4) : -f_inf();
+                qprev = fmaxf(al, bl);
+            }
+        }
+
+        if constexpr (OUT == OUT_LOSS) {
+            // ---- stage 3b (forward): walk my slots ---------------------------------------------------
+            if (finite) {
+#pragma unroll 4
+                for (int s = 0; s < cnt; ++s) {
+                    const float q = fminf(a, b);
+                    const float D = transport_cost<PMODE>(pa, pb, args.p);
+                    float dq = q - qprev;
+                    dq = (q > thr) ? 0.0f : dq;
+                    acc = fmaf(dq, D, acc);
+                    qprev = q;
+                    advance_fwd<POS4>(a, pa, b, pb, adrA, adrB);
+                }
+            }
+        } else if constexpr (OUT == OUT_GRAD) {
+            // ---- stage 3b (gradient): walk + dL/dCDF -----------------------------------------------------
+            // m*d of a tie group is fixed at its first slot; dL/dCDF is nonzero only at a group's LAST
+            // slot: G = (m*d)_group - (m*d)_next group.  It is stored one step later,
+            // when the next slot is known.  (It cannot overwrite the consumed CDF entry or its position:
+            // a slower thread may still load that entry as the head that ends its own range.)
+            if (finite) {
+                float md_prev;
+                bool inherited;  // the open group started before my range: its m*d is not known yet
+                {
+                    const float q = fminf(a, b);
+                    const float D = transport_cost<PMODE>(pa, pb, args.p);
+                    const float fm = (q > thr) ? 0.0f : D;
+                    // what my left neighbour needs to close ITS last slot: my first value and the m*d my
+                    // first slot has if it opens a group (idle thread: the end marker)
+                    sts64(mbox + 8u * tid, cnt > 0 ? q : f_inf(), cnt > 0 ? fm : 0.0f);
+                    inherited = (k0 > 0) && (q == qprev);
+                    md_prev = inherited ? 0.0f : fm;
+                    float dq = q - qprev;
+                    dq = (q > thr) ? 0.0f : dq;
+                    if (cnt > 0) {
+                        acc = fmaf(dq, D, acc);
+                        qprev = q;
+                    }
+                }
+                cta_sync<TPF>();  // mailbox complete (and: every raw bin was read long ago, rows 4/5 are free)
+                uint32_t consumed = 0, fix = NO_FIX;
+                if (cnt > 0) advance<POS4>(a, pa, b, pb, adrA, adrB, consumed);
+                auto step = [&]() {
+                    const float q = fminf(a, b);
+                    const float D = transport_cost<PMODE>(pa, pb, args.p);
+                    const bool over = q > thr;
+                    float dq = q - qprev;
+                    dq = over ? 0.0f : dq;
+                    acc = fmaf(dq, D, acc);
+                    const bool same = (q == qprev);
+                    const float md = same ? md_prev : (over ? 0.0f : D);
+                    sts32o<LY::G_OFF>(consumed, md_prev - md);  // dL/dCDF of the previous slot (0 inside a group)
+                    fix = (inherited && !same) ? consumed : fix;
+                    inherited = inherited && same;
+                    md_prev = md;
+                    qprev = q;
+                    advance<POS4>(a, pa, b, pb, adrA, adrB, consumed);
+                };
+#pragma unroll 4
+                for (int s = 1; s < cnt; ++s) step();
+                float carry_out = -1.0f;  // -1 = "my whole range continues a group opened before me"
+                if (cnt > 0) {
+                    // the slot after my range: first slot of the next thread, or the end marker
+                    float qn, mdn;
+                    lds64(mbox + 8u * (tid + 1), qn, mdn);
+                    const bool same = (qn == qprev);
+                    const float md = same ? md_prev : mdn;
+                    sts32o<LY::G_OFF>(consumed, md_prev - md);
+                    fix = (inherited && !same) ? consumed : fix;
+                    inherited = inherited && same;
+                    carry_out = inherited ? -1.0f : md_prev;
+                }
+                // look-back: add the m*d of a tie group that was opened by an earlier thread
+                sts32(carry + 4u * tid, carry_out);
+                cta_sync<TPF>();
+                if (fix != NO_FIX) {
+                    uint32_t s = carry + 4u * (tid - 1);
+                    float c = lds32(s);
+                    while (c < 0.0f) {  // thread 0 never carries the marker
+                        s -= 4;
+                        c = lds32(s);
+                    }
+                    sts32o<LY::G_OFF>(fix, lds32o<LY::G_OFF>(fix) + c);
+                }
+                cta_sync<TPF>();
+            }
+        } else {
+            // ---- stage 3b (plan): emit qs, lower-bound indices, quantile positions, loss ------------------
+            // Same partition and tie-group rule; the per-group payload is the pair of lower-bound indices
+            // (#{cu < q}, #{cv < q}) -- what `searchsorted(cu, qs)` / `searchsorted(cv, qs)` return
+            // (losses.py:219).
+            if (finite) {
+                int i = i0, j = k0 - i0, is = 0, js = 0, n_inherited = 0;
+                bool inherited = (k0 != 0);
+                for (int s = 0; s < cnt; ++s) {
+                    const float q = fminf(a, b);
+                    const bool take_v = b < a;
+                    if (q != qprev) {
+                        is = i;
+                        js = j;
+                        inherited = false;
+                    }
+                    if (inherited) ++n_inherited;
+                    const long long o = frame * K + k0 + s;
+                    if (args.plan_qs != nullptr) args.plan_qs[o] = q;
+                    if (args.plan_iu != nullptr) args.plan_iu[o] = is;
+                    if (args.plan_iv != nullptr) args.plan_iv[o] = js;
+                    if (args.plan_uq != nullptr) args.plan_uq[o] = lds32(A0 + LY::POS_OFF + 4u * is);
+                    if (args.plan_vq != nullptr) args.plan_vq[o] = lds32(B0 + LY::POS_OFF + 4u * js);
+                    float dq = q - qprev;
+                    dq = (q > thr) ? 0.0f : dq;
+                    acc = fmaf(dq, transport_cost<PMODE>(pa, pb, args.p), acc);
+                    qprev = q;
+                    if (take_v) ++j; else ++i;
+                    advance_fwd<POS4>(a, pa, b, pb, adrA, adrB);
+                }
+                sts32(carry + 4u * tid, __int_as_float((cnt == 0 || inherited) ? -1 : ((is << 16) | js)));
+                cta_sync<TPF>();
+                if (n_inherited > 0) {
+                    uint32_t s = carry + 4u * (tid - 1);
+                    int c = __float_as_int(lds32(s));
+                    while (c < 0) {
+                        s -= 4;
+                        c = __float_as_int(lds32(s));
+                    }
+                    const int is2 = c >> 16, js2 = c & 0xffff;
+                    for (int t = 0; t < n_inherited; ++t) {
+                        const long long o = frame * K + k0 + t;
+                        if (args.plan_iu != nullptr) args.plan_iu[o] = is2;
+                        if (args.plan_iv != nullptr) args.plan_iv[o] = js2;
+                        if (args.plan_uq != nullptr) args.plan_uq[o] = lds32(A0 + LY::POS_OFF + 4u * is2);
+                        if (args.plan_vq != nullptr) args.plan_vq[o] = lds32(B0 + LY::POS_OFF + 4u * js2);
+                    }
+                }
+                if (args.plan_cu != nullptr)
+                    for (int e = tid; e < n; e += TPF) args.plan_cu[frame * n + e] = lds32(A0 + 4u * e);
+                if (args.plan_cv != nullptr)
+                    for (int e = tid; e < m; e += TPF) args.plan_cv[frame * m + e] = lds32(B0 + 4u * e);
+            }
+        }
+
+        // ---- loss of the frame: fp32 partials, summed in fp64 ---------------------------------------
+        {
+            double part = static_cast<double>(acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULL_MASK, part, off);
+            if constexpr (NW > 1) {
+                if ((tid & 31) == 0) scratch[2 * NW + (tid >> 5)] = part;
+                __syncthreads();  // (forward / plan: also "every thread is done with the CDF rows")
+                part = 0.0;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) part += scratch[2 * NW + k];
+            } else {
+                __syncwarp();
+            }
+            if (tid == 0 && args.loss != nullptr) args.loss[frame] = finite ? static_cast<float>(part) : f_nan();
+        }
+
+        const long long next = frame + gridDim.x;
+        if constexpr (!WITH_GRAD) {
+            // the landing zone (CDF rows) is free: fetch the next frame
+            if (tid == 0 && next < args.n_frames) {
+                const Window nu = row_window(args.u, next, n, args.n_frames), nv = row_window(args.v, next, m, args.n_frames);
+                if (nu.bulk && nv.bulk) issue_load(nu, nv);
+            }
+        } else {
+            float og_u[E], og_v[E];  // finished gradient values of my bins
+            if constexpr (MODE == MODE_SPECTRA) {
+                // ---- stage 4: cumsum transpose (suffix sums of dL/dCDF) and the normalisation chain rule.
+                // sum_i gw_i w_i = sum_i (dL/dc_i) c_i (Abel summation), so the mass term needs only the
+                // CDF values and dL/dCDF that are already in shared memory.
+                float lsu[E], lsv[E];
+                float su = 0.0f, sv = 0.0f, du = 0.0f, dv = 0.0f;
+#pragma unroll
+                for (int c = E - 1; c >= 0; --c) {
+                    if (in_u || e0 + c < n) {
+                        const float gq = lds32(A0 + LY::G_OFF + 4 * (e0 + c));
+                        su += gq;
+                        du = fmaf(gq, lds32(A0 + 4 * (e0 + c)), du);
+                    }
+                    lsu[c] = su;
+                    if (in_v || e0 + c < m) {
+                        const float gq = lds32(B0 + LY::G_OFF + 4 * (e0 + c));
+                        sv += gq;
+                        dv = fmaf(gq, lds32(B0 + 4 * (e0 + c)), dv);
+                    }
+                    lsv[c] = sv;
+                }
+                double off_u = static_cast<double>(su), off_v = static_cast<double>(sv), tu, tv;
+                cta_scan1<TPF, true>(off_u, tu, scratch + 4 * NW, tid);
+                cta_scan1<TPF, true>(off_v, tv, scratch + 5 * NW, tid);
+                double dot_u = static_cast<double>(du), dot_v = static_cast<double>(dv);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    dot_u += __shfl_xor_sync(FULL_MASK, dot_u, off);
+                    dot_v += __shfl_xor_sync(FULL_MASK, dot_v, off);
+                }
+                if constexpr (NW > 1) {
+                    if ((tid & 31) == 0) {
+                        scratch[6 * NW + (tid >> 5)] = dot_u;
+                        scratch[7 * NW + (tid >> 5)] = dot_v;
+                    }
+                    __syncthreads();
+                    dot_u = 0.0;
+                    dot_v = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        dot_u += scratch[6 * NW + k];
+                        dot_v += scratch[7 * NW + k];
+                    }
+                }
+                // a clamped mass has no derivative (torch.where picks the constant branch)
+                const double corr_u = u_live ? (cut_scale ? dot_u + dot_v : dot_u) : 0.0;
+                const double corr_v = (!cut_scale && v_live) ? dot_v : 0.0;
+                // gw = offset + local suffix; (offset - corr) is formed in fp64 before rounding
+                const float bu = static_cast<float>(off_u - corr_u), bv = static_cast<float>(off_v - corr_v);
+                const float up = args.upstream != nullptr ? args.upstream[frame] : 1.0f;
+                const float ku = static_cast<float>(inv_u) * up * (square ? 2.0f : 1.0f);
+                const float kv = static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f);
+#pragma unroll
+                for (int c = 0; c < E; ++c) {
+                    float ga = (bu + lsu[c]) * ku;
+                    float gb = (bv + lsv[c]) * kv;
+                    if (square) {
+                        ga *= xu[c];
+                        gb *= xv[c];
+                    }
+                    og_u[c] = finite ? ga : f_nan();
+                    og_v[c] = finite ? gb : f_nan();
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    if (e0 + c < n) sts64(PA0 + 8 * (e0 + c), fminf(xu[c], FLT_BIG), lds32(posU + 4 * c));
-                    if (e0 + c < m) sts64(PB0 + 8 * (e0 + c), fminf(xv[c], FLT_BIG), lds32(posV + 4 * c));
+                    og_u[c] = (e0 + c < n) ? lds32(A0 + LY::G_OFF + 4 * (e0 + c)) : 0.0f;
+                    og_v[c] = (e0 + c < m) ? lds32(B0 + LY::G_OFF + 4 * (e0 + c)) : 0.0f;
                 }
             }
-            if (tid == 0) {
-                sts64(PA0 + 8 * n, f_inf(), lds32(posU + 4 * n));  // tid 0: e0 == 0
-                sts64(PB0 + 8 * m, f_inf(), lds32(posV + 4 * m));
-            }
-            group_sync<TPF>(g);
 
-            if (finite) {
-                // ---- stage 3a: merge-path partition (fixed-trip, branch-free bit descent) --------
-                // i0 = number of u entries among the first k0 merged slots (u first on equal values):
-                // the largest i in [lo, hi] with A[i-1] <= B[k0-i]
-                int i0;
-                {
-                    const int lo = max(0, k0 - m), hi = min(k0, n);
-                    uint32_t cur = PA0 + 8u * lo;  // address of A[i] for the current i
-                    const uint32_t hiA = PA0 + 8u * hi;
-                    const uint32_t sumAB = PA0 + PB0 + 8u * k0;  // addr(A[i]) + addr(B[k0-i]) is constant
+            // ---- stage 5: stage the two gradient rows at their own 16-byte phase and store them ---------
+            float* const ou = args.grad_u != nullptr ? args.grad_u + frame * n : nullptr;
+            float* const ov = args.grad_v != nullptr ? args.grad_v + frame * m : nullptr;
+            const uint32_t lead_u = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ou) & 15);
+            const uint32_t lead_v = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ov) & 15);
+            fence_async_smem();  // order my generic-proxy accesses before the TMA traffic that follows
+            cta_sync<TPF>();     // every thread is done with the CDF rows and with dL/dCDF
+            if (tid == 0 && next < args.n_frames) {  // rows 4/5 are free: prefetch the next frame
+                const Window nu = row_window(args.u, next, n, args.n_frames), nv = row_window(args.v, next, m, args.n_frames);
+                if (nu.bulk && nv.bulk) issue_load(nu, nv);
+            }
 #pragma unroll
-                    for (int step = SEARCH_TOP; step >= 1; step >>= 1) {
-                        const uint32_t cand = cur + 8u * step;
-                        if (cand <= hiA) {
-                            const float av = lds32(cand - 8);      // A[i-1] for the candidate i
-                            const float bv = lds32(sumAB - cand);  // B[k0-i]
-                            if (av <= bv) cur = cand;
-                        }
-                    }
-                    i0 = static_cast<int>((cur - PA0) >> 3);
-                }
-                uint32_t adrA = PA0 + 8u * i0, adrB = PB0 + 8u * (k0 - i0);
-                float a, pa, b, pb;
-                lds64(adrA, a, pa);
-                lds64(adrB, b, pb);
-                float qprev = 0.0f;  // the zero the reference pads in front of qs (losses.py:301)
-                if (k0 > 0) {
-                    const float al = i0 > 0 ? lds32(adrA - 8) : -f_inf();
-                    const float bl = k0 - i0 > 0 ? lds32(adrB - 8) : -f_inf();
-                    qprev = fmaxf(al, bl);
-                }
-
-                if constexpr (OUT == OUT_LOSS) {
-                    // ---- stage 3b (forward): walk my slots ------------------------------------------
-#pragma unroll 4
-                    for (int s = 0; s < cnt; ++s) {
-                        const float q = fminf(a, b);
-                        const float D = transport_cost<PMODE>(pa, pb, args.p);
-                        float dq = q - qprev;
-                        dq = (q > thr) ? 0.0f : dq;
-                        acc = fmaf(dq, D, acc);
-                        qprev = q;
-                        advance_fwd(a, pa, b, pb, adrA, adrB);
-                    }
-                } else if constexpr (OUT == OUT_GRAD) {
-                    // ---- stage 3b (gradient): walk + dL/dCDF in place ---------------------------------
-                    // m*d of a tie group is fixed at its first slot; dL/dCDF is nonzero only at a
-                    // group's LAST slot: G = (m*d)_group - (m*d)_next group.  It is
-                    // stored (into the mirrored dL/dCDF array) one step later, when the next slot is known.
-                    float md_prev;
-                    bool inherited;  // the open group started before my range: its m*d is not known yet
-                    {
-                        const float q = fminf(a, b);
-                        const float D = transport_cost<PMODE>(pa, pb, args.p);
-                        const float fm = (q > thr) ? 0.0f : D;
-                        // what my left neighbour needs to close ITS last slot: my first value and the
-                        // m*d my first slot has if it opens a group (idle thread: the end marker)
-                        sts64(mbox + 8u * tid, cnt > 0 ? q : f_inf(), cnt > 0 ? fm : 0.0f);
-                        inherited = (k0 > 0) && (q == qprev);
-                        md_prev = inherited ? 0.0f : fm;
-                        float dq = q - qprev;
-                        dq = (q > thr) ? 0.0f : dq;
-                        if (cnt > 0) {
-                            acc = fmaf(dq, D, acc);
-                            qprev = q;
-                        }
-                    }
-                    group_sync<TPF>(g);  // mailbox complete before anyone reaches its final peek
-                    uint32_t consumed = 0, fix = NO_FIX;
-                    if (cnt > 0) advance(a, pa, b, pb, adrA, adrB, consumed);
-                    auto step = [&]() {
-                        const float q = fminf(a, b);
-                        const float D = transport_cost<PMODE>(pa, pb, args.p);
-                        const bool over = q > thr;
-                        float dq = q - qprev;
-                        dq = over ? 0.0f : dq;
-                        acc = fmaf(dq, D, acc);
-                        const bool same = (q == qprev);
-                        const float md = same ? md_prev : (over ? 0.0f : D);
-                        sts32((consumed >> 1) + GOFF, md_prev - md);  // dL/dCDF of the previous slot (0 inside a group)
-                        fix = (inherited && !same) ? consumed : fix;
-                        inherited = inherited && same;
-                        md_prev = md;
-                        qprev = q;
-                        advance(a, pa, b, pb, adrA, adrB, consumed);
-                    };
-#pragma unroll 4
-                    for (int s = 1; s < cnt; ++s) step();
-                    float carry_out = -1.0f;  // -1 = "my whole range continues a group opened before me"
-                    if (cnt > 0) {
-                        // the slot after my range: first slot of the next thread, or the end marker
-                        float qn, mdn;
-                        lds64(mbox + 8u * (tid + 1), qn, mdn);
-                        const bool same = (qn == qprev);
-                        const float md = same ? md_prev : mdn;
-                        sts32((consumed >> 1) + GOFF, md_prev - md);
-                        fix = (inherited && !same) ? consumed : fix;
-                        inherited = inherited && same;
-                        carry_out = inherited ? -1.0f : md_prev;
-                    }
-                    // look-back: add the m*d of a tie group that was opened by an earlier thread
-                    sts32(carry + 4u * tid, carry_out);
-                    group_sync<TPF>(g);
-                    if (fix != NO_FIX) {
-                        uint32_t s = carry + 4u * (tid - 1);
-                        float c = lds32(s);
-                        while (c < 0.0f) {  // thread 0 never carries the marker
-                            s -= 4;
-                            c = lds32(s);
-                        }
-                        sts32((fix >> 1) + GOFF, lds32((fix >> 1) + GOFF) + c);
-                    }
-                    group_sync<TPF>(g);
-                } else {
-                    // ---- stage 3b (plan): emit qs, lower-bound indices, quantile positions, loss ------
-                    // Same partition and tie-group rule; the per-group payload is the pair of lower-bound
-                    // indices (#{cu < q}, #{cv < q}) -- what `searchsorted(cu, qs)` / `searchsorted(cv, qs)`
-                    // return (losses.py:219).
-                    int i = i0, j = k0 - i0, is = 0, js = 0, n_inherited = 0;
-                    bool inherited = (k0 != 0);
-                    for (int s = 0; s < cnt; ++s) {
-                        const float q = fminf(a, b);
-                        const bool take_v = b < a;
-                        if (q != qprev) {
-                            is = i;
-                            js = j;
-                            inherited = false;
-                        }
-                        if (inherited) ++n_inherited;
-                        const long long o = frame * K + k0 + s;
-                        if (args.plan_qs != nullptr) args.plan_qs[o] = q;
-                        if (args.plan_iu != nullptr) args.plan_iu[o] = is;
-                        if (args.plan_iv != nullptr) args.plan_iv[o] = js;
-                        if (args.plan_uq != nullptr) args.plan_uq[o] = lds32(PA0 + 8u * is + 4);
-                        if (args.plan_vq != nullptr) args.plan_vq[o] = lds32(PB0 + 8u * js + 4);
-                        float dq = q - qprev;
-                        dq = (q > thr) ? 0.0f : dq;
-                        acc = fmaf(dq, transport_cost<PMODE>(pa, pb, args.p), acc);
-                        qprev = q;
-                        if (take_v) ++j; else ++i;
-                        advance_fwd(a, pa, b, pb, adrA, adrB);
-                    }
-                    sts32(carry + 4u * tid, __int_as_float((cnt == 0 || inherited) ? -1 : ((is << 16) | js)));
-                    group_sync<TPF>(g);
-                    if (n_inherited > 0) {
-                        uint32_t s = carry + 4u * (tid - 1);
-                        int c = __float_as_int(lds32(s));
-                        while (c < 0) {
-                            s -= 4;
-                            c = __float_as_int(lds32(s));
-                        }
-                        const int is2 = c >> 16, js2 = c & 0xffff;
-                        for (int t = 0; t < n_inherited; ++t) {
-                            const long long o = frame * K + k0 + t;
-                            if (args.plan_iu != nullptr) args.plan_iu[o] = is2;
-                            if (args.plan_iv != nullptr) args.plan_iv[o] = js2;
-                            if (args.plan_uq != nullptr) args.plan_uq[o] = lds32(PA0 + 8u * is2 + 4);
-                            if (args.plan_vq != nullptr) args.plan_vq[o] = lds32(PB0 + 8u * js2 + 4);
-                        }
-                    }
-                    if (args.plan_cu != nullptr)
-                        for (int e = tid; e < n; e += TPF) args.plan_cu[frame * n + e] = lds32(PA0 + 8u * e);
-                    if (args.plan_cv != nullptr)
-                        for (int e = tid; e < m; e += TPF) args.plan_cv[frame * m + e] = lds32(PB0 + 8u * e);
-                    group_sync<TPF>(g);  // the pairs are rewritten by the next iteration's stage 2
-                }
-            }  // finite
-
-            // ---- loss of the frame: fp32 partials, summed in fp64 -----------------------------------
+            for (int c = 0; c < E; ++c) {
+                if (in_u || e0 + c < n) sts32(A0 + lead_u + 4 * (e0 + c), og_u[c]);
+                if (in_v || e0 + c < m) sts32(B0 + lead_v + 4 * (e0 + c), og_v[c]);
+            }
+            fence_async_smem();
+            cta_sync<TPF>();
+            // aligned middle by bulk store, the (< 4)-float edges by plain stores
             {
-                double part = static_cast<double>(acc);
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULL_MASK, part, off);
-                if constexpr (NW > 1) {
-                    if ((tid & 31) == 0) scratch[2 * NW + (tid >> 5)] = part;
-                    group_sync<TPF>(g);
-                    part = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NW; ++k) part += scratch[2 * NW + k];
-                }
-                if (tid == 0 && args.loss != nullptr) args.loss[frame] = finite ? static_cast<float>(part) : f_nan();
-            }
-
-            if constexpr (WITH_GRAD) {
-                if constexpr (MODE == MODE_SPECTRA) {
-                    // ---- stage 4: cumsum transpose (suffix sums of dL/dCDF) and the normalisation chain
-                    // rule.  sum_i gw_i w_i = sum_i (dL/dc_i) c_i (Abel summation), so the mass term needs
-                    // only the CDF values and dL/dCDF that are already in shared memory.
-                    const uint32_t GU0 = (PA0 >> 1) + GOFF + 4u * e0, GV0 = (PB0 >> 1) + GOFF + 4u * e0;
-                    float lsu[E], lsv[E];
-                    float su = 0.0f, sv = 0.0f, du = 0.0f, dv = 0.0f;
-#pragma unroll
-                    for (int c = E - 1; c >= 0; --c) {
-                        if (e0 + c < n) {
-                            const float gq = lds32(GU0 + 4 * c);
-                            su += gq;
-                            du = fmaf(gq, lds32(PA0 + 8 * (e0 + c)), du);
-                        }
-                        lsu[c] = su;
-                        if (e0 + c < m) {
-                            const float gq = lds32(GV0 + 4 * c);
-                            sv += gq;
-                            dv = fmaf(gq, lds32(PB0 + 8 * (e0 + c)), dv);
-                        }
-                        lsv[c] = sv;
-                    }
-                    double off_u = static_cast<double>(su), off_v = static_cast<double>(sv), tu, tv;
-                    group_scan1<TPF, true>(off_u, tu, scratch + 4 * NW, tid, g);
-                    group_scan1<TPF, true>(off_v, tv, scratch + 5 * NW, tid, g);
-                    double dot_u = static_cast<double>(du), dot_v = static_cast<double>(dv);
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        dot_u += __shfl_xor_sync(FULL_MASK, dot_u, off);
-                        dot_v += __shfl_xor_sync(FULL_MASK, dot_v, off);
-                    }
-                    if constexpr (NW > 1) {
-                        if ((tid & 31) == 0) {
-                            scratch[6 * NW + (tid >> 5)] = dot_u;
-                            scratch[7 * NW + (tid >> 5)] = dot_v;
-                        }
-                        group_sync<TPF>(g);
-                        dot_u = 0.0;
-                        dot_v = 0.0;
-#pragma unroll
-                        for (int k = 0; k < NW; ++k) {
-                            dot_u += scratch[6 * NW + k];
-                            dot_v += scratch[7 * NW + k];
-                        }
-                    }
-                    // a clamped mass has no derivative (torch.where picks the constant branch)
-                    const double corr_u = u_live ? (cut_scale ? dot_u + dot_v : dot_u) : 0.0;
-                    const double corr_v = (!cut_scale && v_live) ? dot_v : 0.0;
-                    // gw = offset + local suffix; (offset - corr) is formed in fp64 before rounding
-                    const float bu = static_cast<float>(off_u - corr_u), bv = static_cast<float>(off_v - corr_v);
-                    const float up = args.upstream != nullptr ? args.upstream[frame] : 1.0f;
-                    const float ku = static_cast<float>(inv_u) * up * (square ? 2.0f : 1.0f);
-                    const float kv = static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f);
-#pragma unroll
-                    for (int c = 0; c < E; ++c) {
-                        float ga = (bu + lsu[c]) * ku;
-                        float gb = (bv + lsv[c]) * kv;
-                        if (square) {
-                            ga *= xu[c];
-                            gb *= xv[c];
-                        }
-                        og_u[c] = finite ? ga : f_nan();
-                        og_v[c] = finite ? gb : f_nan();
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < E; ++c) {
-                        og_u[c] = (e0 + c < n) ? lds32((PA0 >> 1) + GOFF + 4 * (e0 + c)) : 0.0f;
-                        og_v[c] = (e0 + c < m) ? lds32((PB0 >> 1) + GOFF + 4 * (e0 + c)) : 0.0f;
-                    }
-                }
-            }
-        }  // active
-
-        // ---- stage 5: stage the gradient rows (FPC rows back to back) and store them -------------
-        if constexpr (WITH_GRAD) {
-            float* const ou = args.grad_u != nullptr ? args.grad_u + frame0 * n : nullptr;
-            float* const ov = args.grad_v != nullptr ? args.grad_v + frame0 * m : nullptr;
-            const bool bulk_out = out_aligned && (nfr == FPC);
-            fence_async_smem();  // order my generic-proxy accesses to LAND / PAIRS before the TMA that follows
-            __syncthreads();     // every group is done with its pairs and its dL/dCDF array
-            {
-                const long long next = quad + gridDim.x;
-                if (threadIdx.x == 0 && next < n_quads && quad_is_bulk(next)) issue_load(next);
-            }
-            if (active) {
-#pragma unroll
-                for (int c = 0; c < E; ++c) {
-                    if (e0 + c < n) outf[g * n + e0 + c] = og_u[c];
-                    if (e0 + c < m) outf[FPC * n + g * m + e0 + c] = og_v[c];
-                }
-            }
-            if (bulk_out) fence_async_smem();
-            __syncthreads();
-            if (bulk_out) {
-                if (threadIdx.x == 0) {
-                    if (ou != nullptr) bulk_s2g(ou, outf, 4u * FPC * n);
-                    if (ov != nullptr) bulk_s2g(ov, outf + FPC * n, 4u * FPC * m);
+                const uint32_t head_u = min((16u - lead_u) & 15u, 4u * n);  // bytes before the aligned middle
+                const uint32_t head_v = min((16u - lead_v) & 15u, 4u * m);
+                const uint32_t body_u = (4u * n - head_u) & ~15u, body_v = (4u * m - head_v) & ~15u;
+                if (tid == 0) {
+                    if (ou != nullptr && body_u > 0)
+                        bulk_s2g(reinterpret_cast<char*>(ou) + head_u, smem + LY::A + lead_u + head_u, body_u);
+                    if (ov != nullptr && body_v > 0)
+                        bulk_s2g(reinterpret_cast<char*>(ov) + head_v, smem + LY::B + lead_v + head_v, body_v);
                     bulk_commit();
                 }
-            } else {
-                if (ou != nullptr)
-                    for (int idx = threadIdx.x; idx < nfr * n; idx += NT) ou[idx] = outf[idx];
-                if (ov != nullptr)
-                    for (int idx = threadIdx.x; idx < nfr * m; idx += NT) ov[idx] = outf[FPC * n + idx];
-                __syncthreads();  // the plain stores have read the staging area
+                if (tid < 8 && ou != nullptr) {  // threads 0-3: head floats, 4-7: tail floats
+                    const int hf = static_cast<int>(head_u >> 2), tf = n - hf - static_cast<int>(body_u >> 2);
+                    const int idx = tid < 4 ? tid : n - tf + (tid - 4);
+                    if (tid < 4 ? (tid < hf) : (tid - 4 < tf)) ou[idx] = lds32(A0 + lead_u + 4u * idx);
+                }
+                if (tid >= 8 && tid < 16 && ov != nullptr) {
+                    const int t8 = tid - 8;
+                    const int hf = static_cast<int>(head_v >> 2), tf = m - hf - static_cast<int>(body_v >> 2);
+                    const int idx = t8 < 4 ? t8 : m - tf + (t8 - 4);
+                    if (t8 < 4 ? (t8 < hf) : (t8 - 4 < tf)) ov[idx] = lds32(B0 + lead_v + 4u * idx);
+                }
             }
         }
     }
     if constexpr (WITH_GRAD) {
-        if (threadIdx.x == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store
+        if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store
     }
 }
 
