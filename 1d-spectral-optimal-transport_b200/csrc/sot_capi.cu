@@ -79,8 +79,8 @@ struct Config {
 const Config kConfigs[] = {
     {32, 9, 296, sot_launch_32_9_296},        // <= 288 bins   (n_fft 512: 257)
     {64, 9, 584, sot_launch_64_9_584},        // <= 576 bins   (n_fft 1024: 513)
-    {128, 9, 1032, sot_launch_128_9_1032},    // <= 1025 bins  (n_fft 2048: 1025)
-    {64, 17, 1032, sot_launch_64_17_1032},    //               alternative shapes for 1025 (tuning)
+    {64, 17, 1032, sot_launch_64_17_1032},    // <= 1025 bins  (n_fft 2048: 1025); measured best of the three
+    {128, 9, 1032, sot_launch_128_9_1032},    //               alternative shapes for 1025 (tuning)
     {32, 33, 1064, sot_launch_32_33_1064},
     {128, 9, 1160, sot_launch_128_9_1160},    // <= 1152 bins
     {128, 17, 2184, sot_launch_128_17_2184},  // <= 2176 bins  (n_fft 4096: 2049)

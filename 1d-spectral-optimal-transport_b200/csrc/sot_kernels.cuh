@@ -228,23 +228,22 @@ __host__ __device__ constexpr int ilog2_ceil(int x) {
     return b;
 }
 
-// 16-byte aligned window around row `f` of a [frames, width] fp32 array
-struct Window {
-    const char* src;  // aligned start
-    uint32_t lead;    // bytes between the window start and the row start (0, 4, 8, 12)
-    uint32_t bytes;   // window size, multiple of 16
-    bool bulk;        // the window lies inside the array: safe to fetch with a bulk copy
-};
-SOT_DEVINL Window row_window(const float* base, long long f, int width, long long frames) {
-    const uintptr_t row = reinterpret_cast<uintptr_t>(base + f * width);
-    const uintptr_t start = row & ~static_cast<uintptr_t>(15);
-    Window w;
-    w.src = reinterpret_cast<const char*>(start);
-    w.lead = static_cast<uint32_t>(row - start);
-    w.bytes = (w.lead + 4u * width + 15u) & ~15u;
-    w.bulk = start >= reinterpret_cast<uintptr_t>(base) &&
-             start + w.bytes <= reinterpret_cast<uintptr_t>(base + frames * width);
-    return w;
+// 16-byte aligned window around row `f` of a [frames, width] fp32 array: `lead` bytes (0, 4, 8, 12)
+// sit between the window start and the row.  Only the low address bits matter for the phase, so
+// every thread gets it with a few 32-bit operations; the elected thread builds the 64-bit source.
+SOT_DEVINL uint32_t row_lead(const float* base, long long f, int width) {
+    return (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(base)) +
+            4u * static_cast<uint32_t>(width) * static_cast<uint32_t>(f)) & 15u;
+}
+// the window of row f lies inside the array (safe to fetch with a bulk copy): always true except
+// for the first row of an array that does not start, and the last row of one that does not end,
+// on a 16-byte boundary
+SOT_DEVINL bool row_is_bulk(const float* base, long long f, int width, long long frames) {
+    const uint32_t lo = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(base));
+    const bool head_ok = (f > 0) || ((lo & 15u) == 0);
+    const bool tail_ok = (f + 1 < frames) ||
+                         (((lo + 4u * static_cast<uint32_t>(width) * static_cast<uint32_t>(frames)) & 15u) == 0);
+    return head_ok && tail_ok;
 }
 
 template <int TPF, int E, int RS, int PMODE, int OUT, int MODE>
@@ -295,35 +294,46 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
     }
     __syncthreads();
 
-    auto issue_load = [&](const Window& wu, const Window& wv) {  // one elected thread
-        mbar_expect_tx(mbar, wu.bytes + wv.bytes);
-        bulk_g2s(smem + LAND, wu.src, wu.bytes, mbar);
-        bulk_g2s(smem + LAND + LY::ROW, wv.src, wv.bytes, mbar);
+    auto issue_load = [&](long long f, uint32_t lu, uint32_t lv) {  // one elected thread
+        const uint32_t bu = (lu + 4u * n + 15u) & ~15u, bv = (lv + 4u * m + 15u) & ~15u;
+        mbar_expect_tx(mbar, bu + bv);
+        bulk_g2s(smem + LAND, reinterpret_cast<const char*>(args.u + f * n) - lu, bu, mbar);
+        bulk_g2s(smem + LAND + LY::ROW, reinterpret_cast<const char*>(args.v + f * m) - lv, bv, mbar);
     };
 
     long long frame = blockIdx.x;
     uint32_t parity = 0;
-    if (frame < args.n_frames && tid == 0) {
-        const Window wu = row_window(args.u, frame, n, args.n_frames), wv = row_window(args.v, frame, m, args.n_frames);
-        if (wu.bulk && wv.bulk) issue_load(wu, wv);
+    // state of the frame in flight: phases of its two rows and whether it comes by bulk copy
+    uint32_t lead_in_u = 0, lead_in_v = 0;
+    bool bulk_in = false;
+    if (frame < args.n_frames) {
+        lead_in_u = row_lead(args.u, frame, n);
+        lead_in_v = row_lead(args.v, frame, m);
+        bulk_in = row_is_bulk(args.u, frame, n, args.n_frames) && row_is_bulk(args.v, frame, m, args.n_frames);
+        if (bulk_in && tid == 0) issue_load(frame, lead_in_u, lead_in_v);
     }
 
     for (; frame < args.n_frames; frame += gridDim.x) {
         // ---- stage 0: the frame's raw rows are (or get) in the landing zone ----------------------
-        const Window wu = row_window(args.u, frame, n, args.n_frames), wv = row_window(args.v, frame, m, args.n_frames);
-        const bool bulk_in = wu.bulk && wv.bulk;
         uint32_t rawU = sb + LAND + 4u * e0, rawV = sb + LAND + LY::ROW + 4u * e0;  // my first raw bins
         if (bulk_in) {
             mbar_wait(mbar, parity);
             parity ^= 1;
-            rawU += wu.lead;
-            rawV += wv.lead;
+            rawU += lead_in_u;
+            rawV += lead_in_v;
         } else {  // first / last row of an array whose ends are not 16-byte aligned: plain coalesced loads
             const float* gu = args.u + frame * n;
             const float* gv = args.v + frame * m;
             for (int idx = tid; idx < n; idx += TPF) fsm[LAND / 4 + idx] = gu[idx];
             for (int idx = tid; idx < m; idx += TPF) fsm[LAND / 4 + RS + idx] = gv[idx];
             cta_sync<TPF>();
+        }
+        // the frame after this one (its load is issued further down, when the landing zone is free)
+        const long long next = frame + gridDim.x;
+        if (next < args.n_frames) {
+            lead_in_u = row_lead(args.u, next, n);
+            lead_in_v = row_lead(args.v, next, m);
+            bulk_in = row_is_bulk(args.u, next, n, args.n_frames) && row_is_bulk(args.v, next, m, args.n_frames);
         }
         if (!pos_shared) {  // per-frame supports
             const float* gpu = args.pos_u + frame * args.pos_u_stride;
@@ -354,8 +364,13 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
             {
                 double t = 0.0;
 #pragma unroll
+                for (int c = 0; c < E; ++c) xu[c] = lds32(rawU + 4 * c);  // (past the row: finite garbage inside the landing rows)
+                if (!in_u) {
+#pragma unroll
+                    for (int c = 0; c < E; ++c) xu[c] = (e0 + c < n) ? xu[c] : 0.0f;
+                }
+#pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    xu[c] = (in_u || e0 + c < n) ? lds32(rawU + 4 * c) : 0.0f;
                     t += static_cast<double>(square ? xu[c] * xu[c] : xu[c]);
                     P[c] = t;
                 }
@@ -366,15 +381,25 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
                 inv_u = recip_f64(u_live ? mass_u : SAFE_EPS);
                 if (args.flags & FLAG_RAW) inv_u = 1.0;
                 if constexpr (NW == 1) __syncwarp();
+                if (in_u) {
 #pragma unroll
-                for (int c = 0; c < E; ++c)
-                    if (in_u || e0 + c < n) sts32(A0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_u));
+                    for (int c = 0; c < E; ++c) sts32(A0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_u));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < E; ++c)
+                        if (e0 + c < n) sts32(A0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_u));
+                }
             }
             {
                 double t = 0.0;
 #pragma unroll
+                for (int c = 0; c < E; ++c) xv[c] = lds32(rawV + 4 * c);
+                if (!in_v) {
+#pragma unroll
+                    for (int c = 0; c < E; ++c) xv[c] = (e0 + c < m) ? xv[c] : 0.0f;
+                }
+#pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    xv[c] = (in_v || e0 + c < m) ? lds32(rawV + 4 * c) : 0.0f;
                     t += static_cast<double>(square ? xv[c] * xv[c] : xv[c]);
                     P[c] = t;
                 }
@@ -388,9 +413,14 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
                     u_live = v_live = false;
                 }
                 if constexpr (NW == 1) __syncwarp();
+                if (in_v) {
 #pragma unroll
-                for (int c = 0; c < E; ++c)
-                    if (in_v || e0 + c < m) sts32(B0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_v));
+                    for (int c = 0; c < E; ++c) sts32(B0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_v));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < E; ++c)
+                        if (e0 + c < m) sts32(B0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_v));
+                }
             }
             // NaN / inf anywhere (or an overflowing cut-mode scale) poisons the frame: the walk is skipped
             // (its +inf sentinels must stay unique) and NaN is written instead
@@ -609,13 +639,9 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
             if (tid == 0 && args.loss != nullptr) args.loss[frame] = finite ? static_cast<float>(part) : f_nan();
         }
 
-        const long long next = frame + gridDim.x;
         if constexpr (!WITH_GRAD) {
             // the landing zone (CDF rows) is free: fetch the next frame
-            if (tid == 0 && next < args.n_frames) {
-                const Window nu = row_window(args.u, next, n, args.n_frames), nv = row_window(args.v, next, m, args.n_frames);
-                if (nu.bulk && nv.bulk) issue_load(nu, nv);
-            }
+            if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
         } else {
             float og_u[E], og_v[E];  // finished gradient values of my bins
             if constexpr (MODE == MODE_SPECTRA) {
@@ -696,10 +722,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
             const uint32_t lead_v = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ov) & 15);
             fence_async_smem();  // order my generic-proxy accesses before the TMA traffic that follows
             cta_sync<TPF>();     // every thread is done with the CDF rows and with dL/dCDF
-            if (tid == 0 && next < args.n_frames) {  // rows 4/5 are free: prefetch the next frame
-                const Window nu = row_window(args.u, next, n, args.n_frames), nv = row_window(args.v, next, m, args.n_frames);
-                if (nu.bulk && nv.bulk) issue_load(nu, nv);
-            }
+            if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);  // rows 4/5 are free
 #pragma unroll
             for (int c = 0; c < E; ++c) {
                 if (in_u || e0 + c < n) sts32(A0 + lead_u + 4 * (e0 + c), og_u[c]);

@@ -26,18 +26,26 @@ class _GlobalMean(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rows, group):
-        stats = torch.stack((rows.sum(dtype=torch.float64),
-                             torch.tensor(float(rows.numel()), dtype=torch.float64, device=rows.device)))
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
-        ctx.save_for_backward(stats[1:2])
+        total = rows.sum(dtype=torch.float64)
+        count = float(rows.numel())
         ctx.shape, ctx.dtype = rows.shape, rows.dtype
-        return (stats[0] / stats[1]).to(rows.dtype)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            # (no host->device copy here: `torch.tensor(count, device=...)` would synchronise the stream)
+            stats = torch.stack((total, torch.full_like(total, count)))
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+            ctx.save_for_backward(stats[1:2])
+            ctx.count = None
+            return (stats[0] / stats[1]).to(rows.dtype)
+        ctx.count = count
+        return (total / count).to(rows.dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
-        (count,) = ctx.saved_tensors
-        g = (grad_out.to(torch.float64) / count).to(ctx.dtype)
+        if ctx.count is None:
+            (count,) = ctx.saved_tensors
+            g = (grad_out.to(torch.float64) / count).to(ctx.dtype)
+        else:
+            g = grad_out / ctx.count
         return g.expand(ctx.shape), None
 
 

@@ -193,11 +193,13 @@ def main():
     sampler.start()
     launches0 = _capi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` sees exactly the timed steps
     ev0.record()
     for _ in range(args.steps):
         value = step()
     ev1.record()
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     launches = _capi.launch_count() - launches0
     ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
