@@ -52,7 +52,7 @@ SIGNATURES = {
     "sot_abi_version": (ctypes.c_int, []),
     "sot_last_error": (ctypes.c_char_p, []),
     "sot_max_bins": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32]),
-    "sot_set_tuning": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32]),
+    "sot_set_tuning": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "sot_launch_count": (ctypes.c_int64, []),
 }
 
@@ -246,8 +246,8 @@ def loss_grad_host(u, v, pos_u, pos_v, p, flags, upstream=None, want_loss=True, 
     return loss, gu, gv
 
 
-def set_tuning(threads_per_frame: int = 0, bins_per_thread: int = 0):
-    _check(load().sot_set_tuning(threads_per_frame, bins_per_thread))
+def set_tuning(threads_per_frame: int = 0, bins_per_thread: int = 0, chains_per_thread: int = 0):
+    _check(load().sot_set_tuning(threads_per_frame, bins_per_thread, chains_per_thread))
 
 
 def launch_count() -> int:

@@ -11,15 +11,17 @@
 #include "../../include/sot_b200.h"
 #include "sot_launch.cuh"
 
-SOT_DECLARE_CONFIG(32, 9, 296)
-SOT_DECLARE_CONFIG(64, 9, 584)
-SOT_DECLARE_CONFIG(128, 9, 1032)
-SOT_DECLARE_CONFIG(64, 17, 1032)
-SOT_DECLARE_CONFIG(32, 33, 1064)
-SOT_DECLARE_CONFIG(128, 9, 1160)
-SOT_DECLARE_CONFIG(128, 17, 2184)
-SOT_DECLARE_CONFIG(256, 17, 4360)
-SOT_DECLARE_CONFIG(256, 33, 8456)
+SOT_DECLARE_CONFIG(32, 9, 296, 2)
+SOT_DECLARE_CONFIG(32, 9, 296, 1)
+SOT_DECLARE_CONFIG(64, 9, 584, 2)
+SOT_DECLARE_CONFIG(64, 17, 1032, 2)
+SOT_DECLARE_CONFIG(64, 17, 1032, 1)
+SOT_DECLARE_CONFIG(128, 9, 1032, 1)
+SOT_DECLARE_CONFIG(32, 33, 1064, 2)
+SOT_DECLARE_CONFIG(128, 9, 1160, 1)
+SOT_DECLARE_CONFIG(128, 17, 2184, 2)
+SOT_DECLARE_CONFIG(256, 17, 4360, 2)
+SOT_DECLARE_CONFIG(256, 33, 8456, 1)
 
 namespace sot {
 // ------------------------------------------------------------------------------------------
@@ -70,28 +72,30 @@ namespace {
 
 using LaunchFn = cudaError_t (*)(const sot::LaunchRequest&, cudaStream_t);
 struct Config {
-    int tpf, e, rs;
+    int tpf, e, rs, nch;
     LaunchFn fn;
     int max_bins() const { return tpf * e < rs - 7 ? tpf * e : rs - 7; }
 };
 // Ordered by preference for a given row length: the first entry that holds the row is used
 // (choices from measurements on B200, profiles/).  Shared memory per CTA = (4 or 6) * 4 * rs bytes.
 const Config kConfigs[] = {
-    {32, 9, 296, sot_launch_32_9_296},        // <= 288 bins   (n_fft 512: 257)
-    {64, 9, 584, sot_launch_64_9_584},        // <= 576 bins   (n_fft 1024: 513)
-    {64, 17, 1032, sot_launch_64_17_1032},    // <= 1025 bins  (n_fft 2048: 1025); measured best of the three
-    {128, 9, 1032, sot_launch_128_9_1032},    //               alternative shapes for 1025 (tuning)
-    {32, 33, 1064, sot_launch_32_33_1064},
-    {128, 9, 1160, sot_launch_128_9_1160},    // <= 1152 bins
-    {128, 17, 2184, sot_launch_128_17_2184},  // <= 2176 bins  (n_fft 4096: 2049)
-    {256, 17, 4360, sot_launch_256_17_4360},  // <= 4352 bins  (n_fft 8192: 4097)
-    {256, 33, 8456, sot_launch_256_33_8456},  // <= 8448 bins  (n_fft 16384: 8193)
+    {32, 9, 296, 1, sot_launch_32_9_296_1},      // <= 288 bins   (n_fft 512: 257)
+    {32, 9, 296, 2, sot_launch_32_9_296_2},      //               (two-chain variant, tuning only: measured slower)
+    {64, 9, 584, 2, sot_launch_64_9_584_2},      // <= 576 bins   (n_fft 1024: 513)
+    {64, 17, 1032, 1, sot_launch_64_17_1032_1},  // <= 1025 bins  (n_fft 2048: 1025) -- measured best of the five
+    {64, 17, 1032, 2, sot_launch_64_17_1032_2},  //               (tuning alternatives for 1025)
+    {128, 9, 1032, 1, sot_launch_128_9_1032_1},
+    {32, 33, 1064, 2, sot_launch_32_33_1064_2},
+    {128, 9, 1160, 1, sot_launch_128_9_1160_1},    // <= 1152 bins
+    {128, 17, 2184, 2, sot_launch_128_17_2184_2},  // <= 2176 bins  (n_fft 4096: 2049)
+    {256, 17, 4360, 2, sot_launch_256_17_4360_2},  // <= 4352 bins  (n_fft 8192: 4097)
+    {256, 33, 8456, 1, sot_launch_256_33_8456_1},  // <= 8448 bins  (n_fft 16384: 8193)
 };
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 
 thread_local char g_error[512] = "";
 std::atomic<long long> g_launches{0};
-std::atomic<int> g_tune_tpf{0}, g_tune_e{0};
+std::atomic<int> g_tune_tpf{0}, g_tune_e{0}, g_tune_nch{0};
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -111,7 +115,8 @@ const Config* pick_config(int n, int m) {
     if (tt != 0) {
         for (int i = 0; i < kNumConfigs; ++i) {
             const Config& c = kConfigs[i];
-            if (c.tpf == tt && c.e == te && c.max_bins() >= need) return &c;
+            if (c.tpf == tt && c.e == te && (g_tune_nch.load() == 0 || c.nch == g_tune_nch.load()) && c.max_bins() >= need)
+                return &c;
         }
     }
     for (int i = 0; i < kNumConfigs; ++i)
@@ -173,19 +178,22 @@ int sot_abi_version(void) { return SOT_B200_ABI_VERSION; }
 const char* sot_last_error(void) { return g_error; }
 int64_t sot_launch_count(void) { return g_launches.load(); }
 
-int sot_set_tuning(int32_t tpf, int32_t e) {
+int sot_set_tuning(int32_t tpf, int32_t e, int32_t chains) {
     if (tpf == 0 && e == 0) {
         g_tune_tpf = 0;
         g_tune_e = 0;
+        g_tune_nch = 0;
         return SOT_OK;
     }
     for (int i = 0; i < kNumConfigs; ++i)
-        if (kConfigs[i].tpf == tpf && kConfigs[i].e == e) {
+        if (kConfigs[i].tpf == tpf && kConfigs[i].e == e && (chains == 0 || kConfigs[i].nch == chains)) {
             g_tune_tpf = tpf;
             g_tune_e = e;
+            g_tune_nch = chains;
             return SOT_OK;
         }
-    return fail(SOT_EINVAL, "no kernel configuration with %d threads per frame and %d bins per thread", tpf, e);
+    return fail(SOT_EINVAL, "no kernel configuration with %d threads per frame, %d bins per thread, %d chain(s)", tpf,
+                e, chains);
 }
 
 int sot_max_bins(int32_t /*with_grad*/, int32_t /*shared_positions*/) {

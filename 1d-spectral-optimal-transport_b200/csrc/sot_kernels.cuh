@@ -29,6 +29,8 @@
 // Thread t owns the E consecutive bins [t*E, t*E+E) of both rows ("blocked"); E is odd so every
 // blocked access of a warp is bank-conflict free.
 #pragma once
+#include <type_traits>
+
 #include "sot_device.cuh"
 
 namespace sot {
@@ -83,7 +85,7 @@ SOT_DEVINL float f_inf() { return __int_as_float(0x7f800000); }
 SOT_DEVINL float f_nan() { return __int_as_float(0x7fc00000); }
 
 // ---- compile-time shared-memory layout ---------------------------------------------------------
-template <int TPF, int RS, int OUT>
+template <int TPF, int RS, int OUT, int NCH>
 struct Layout {
     static constexpr uint32_t ROW = 4u * RS;
     static constexpr uint32_t A = 0, B = ROW;     // CDF rows (also forward landing zone / output staging)
@@ -91,9 +93,9 @@ struct Layout {
     static constexpr uint32_t G_OFF = 4 * ROW;    // cdf address -> dL/dCDF address
     static constexpr uint32_t ROWS = (OUT == OUT_GRAD) ? 6 : 4;
     static constexpr uint32_t SCRATCH = ROWS * ROW;               // 8 doubles per warp
-    static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per thread + end marker
-    static constexpr uint32_t CARRY = MBOX + 8u * (TPF + 1);
-    static constexpr uint32_t MBAR = (CARRY + 4u * TPF + 15u) & ~15u;
+    static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per chunk + end marker
+    static constexpr uint32_t CARRY = MBOX + 8u * (NCH * TPF + 1);
+    static constexpr uint32_t MBAR = (CARRY + 4u * NCH * TPF + 15u) & ~15u;
     static constexpr uint32_t TOTAL = MBAR + 16u;
     static constexpr int MAX_BINS = RS - 7;  // sentinel + up to 3 floats of lead + rounding of the bulk window
 };
@@ -246,10 +248,15 @@ SOT_DEVINL bool row_is_bulk(const float* base, long long f, int width, long long
     return head_ok && tail_ok;
 }
 
-template <int TPF, int E, int RS, int PMODE, int OUT, int MODE>
-__global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TOTAL, OUT))
+template <int N>
+using IC = std::integral_constant<int, N>;
+
+template <int TPF, int E, int RS, int NCH, int PMODE, int OUT, int MODE>
+__global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH>::TOTAL, OUT))
     sot_frame_kernel(const FrameArgs args) {
-    using LY = Layout<TPF, RS, OUT>;
+    static_assert(NCH == 1 || NCH == 2, "one or two merge chains per thread");
+    using LY = Layout<TPF, RS, OUT, NCH>;
+    constexpr int NCHUNK = NCH * TPF;
     constexpr bool WITH_GRAD = (OUT == OUT_GRAD);
     constexpr int NW = TPF / 32;
     constexpr int SEARCH_TOP = 1 << (ilog2_ceil(TPF * E + 1) - 1);
@@ -276,17 +283,24 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
     const uint32_t mbox = sb + LY::MBOX, carry = sb + LY::CARRY;
     const bool in_u = e0 + E <= n, in_v = e0 + E <= m;  // all of my E bins exist (no guards needed)
 
-    // L consecutive merged slots per thread.  L is ODD on purpose: for a balanced merge thread t starts
-    // near entry L*t/2 of each row, and an even L would put the lanes of a warp on few distinct banks
-    // (measured: 8-way conflicts on every load of the walk); odd L spreads them.
-    const int L = ((K + TPF - 1) / TPF) | 1;
-    const int k0 = min(tid * L, K);
-    const int cnt = min(L, K - k0);
+    // The K merged slots are cut into NCH * TPF chunks of L consecutive slots; thread t walks chunks
+    // NCH*t .. NCH*t + NCH-1 AT THE SAME TIME (NCH independent dependency chains: the walk is a chain of
+    // dependent shared-memory loads, and with few resident warps instruction-level parallelism is what
+    // hides their latency).  L is ODD on purpose: for a balanced merge chunk c starts near entry L*c/2
+    // of each row, and an even L would put the lanes of a warp on few distinct banks (measured: 8-way
+    // conflicts on every load of the walk); odd L spreads them.
+    const int L = ((K + NCHUNK - 1) / NCHUNK) | 1;
+    int k0[NCH], cnt[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        k0[ch] = min((NCH * tid + ch) * L, K);
+        cnt[ch] = min(L, K - k0[ch]);  // non-increasing in the chunk index
+    }
 
     if (tid == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
-        sts64(mbox + 8u * TPF, f_inf(), 0.0f);  // virtual slot K: a new group with m*d = 0
+        sts64(mbox + 8u * NCHUNK, f_inf(), 0.0f);  // virtual slot K: a new group with m*d = 0
     }
     if (pos_shared) {  // positions once per CTA
         for (int idx = tid; idx <= n; idx += TPF) fsm[2 * RS + idx] = args.pos_u[min(idx, n - 1)];
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
             if (tid == 0) bulk_wait_read_all();
         }
 
-        float acc = 0.0f;    // my part of the frame's loss
+        float acc[NCH] = {};  // my part of the frame's loss
         bool finite = true;  // masses (and the scaled totals) are finite numbers
         double inv_u = 1.0, inv_v = 1.0;
         bool u_live = false, v_live = false;  // mass above the safe_divide floor -> carries gradient
@@ -445,55 +459,79 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
         }
         cta_sync<TPF>();
 
-        uint32_t adrA = A0, adrB = B0;
-        float a = 0.0f, pa = 0.0f, b = 0.0f, pb = 0.0f, qprev = 0.0f;
-        int i0 = 0;
+        uint32_t adrA[NCH], adrB[NCH];
+        float a[NCH], pa[NCH], b[NCH], pb[NCH], qprev[NCH];
+        int i0[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            adrA[ch] = A0;
+            adrB[ch] = B0;
+            a[ch] = pa[ch] = b[ch] = pb[ch] = qprev[ch] = 0.0f;
+            i0[ch] = 0;
+        }
         if (finite) {
             // ---- stage 3a: merge-path partition (fixed-trip, branch-free bit descent) ---------------
             // i0 = number of u entries among the first k0 merged slots (u first on equal values):
-            // the largest i in [lo, hi] with A[i-1] <= B[k0-i]
-            {
-                const int lo = max(0, k0 - m), hi = min(k0, n);
-                uint32_t cur = A0 + 4u * lo;  // address of A[i] for the current i
-                const uint32_t hiA = A0 + 4u * hi;
-                const uint32_t sumAB = A0 + B0 + 4u * k0;  // addr(A[i]) + addr(B[k0-i]) is constant
+            // the largest i in [lo, hi] with A[i-1] <= B[k0-i].  The NCH searches are interleaved.
+            uint32_t cur[NCH], hiA[NCH], sumAB[NCH];
 #pragma unroll
-                for (int step = SEARCH_TOP; step >= 1; step >>= 1) {
-                    const uint32_t cand = cur + 4u * step;
-                    if (cand <= hiA) {
-                        const float av = lds32(cand - 4);      // A[i-1] for the candidate i
-                        const float bv = lds32(sumAB - cand);  // B[k0-i]
-                        if (av <= bv) cur = cand;
+            for (int ch = 0; ch < NCH; ++ch) {
+                cur[ch] = A0 + 4u * max(0, k0[ch] - m);  // address of A[i] for the current i
+                hiA[ch] = A0 + 4u * min(k0[ch], n);
+                sumAB[ch] = A0 + B0 + 4u * k0[ch];  // addr(A[i]) + addr(B[k0-i]) is constant
+            }
+#pragma unroll
+            for (int step = SEARCH_TOP; step >= 1; step >>= 1) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const uint32_t cand = cur[ch] + 4u * step;
+                    if (cand <= hiA[ch]) {
+                        const float av = lds32(cand - 4);          // A[i-1] for the candidate i
+                        const float bv = lds32(sumAB[ch] - cand);  // B[k0-i]
+                        if (av <= bv) cur[ch] = cand;
                     }
                 }
-                i0 = static_cast<int>((cur - A0) >> 2);
             }
-            adrA = A0 + 4u * i0;
-            adrB = B0 + 4u * (k0 - i0);
-            a = lds32(adrA);
-            pa = lds32o<LY::POS_OFF>(adrA);
-            b = lds32(adrB);
-            pb = lds32o<LY::POS_OFF>(adrB);
-            if (k0 > 0) {  // else: the zero the reference pads in front of qs (losses.py:301)
-                const float al = i0 > 0 ? lds32(adrA - 4) : -f_inf();
-                const float bl = k0 - i0 > 0 ? lds32(adrB - 4) : -f_inf();
-                qprev = fmaxf(al, bl);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                i0[ch] = static_cast<int>((cur[ch] - A0) >> 2);
+                adrA[ch] = A0 + 4u * i0[ch];
+                adrB[ch] = B0 + 4u * (k0[ch] - i0[ch]);
+                a[ch] = lds32(adrA[ch]);
+                pa[ch] = lds32o<LY::POS_OFF>(adrA[ch]);
+                b[ch] = lds32(adrB[ch]);
+                pb[ch] = lds32o<LY::POS_OFF>(adrB[ch]);
+                if (k0[ch] > 0) {  // else: the zero the reference pads in front of qs (losses.py:301)
+                    const float al = i0[ch] > 0 ? lds32(adrA[ch] - 4) : -f_inf();
+                    const float bl = k0[ch] - i0[ch] > 0 ? lds32(adrB[ch] - 4) : -f_inf();
+                    qprev[ch] = fmaxf(al, bl);
+                }
             }
         }
 
         if constexpr (OUT == OUT_LOSS) {
             // ---- stage 3b (forward): walk my slots ---------------------------------------------------
             if (finite) {
-#pragma unroll 4
-                for (int s = 0; s < cnt; ++s) {
-                    const float q = fminf(a, b);
-                    const float D = transport_cost<PMODE>(pa, pb, args.p);
-                    float dq = q - qprev;
+                auto fstep = [&](auto CH) {
+                    constexpr int ch = decltype(CH)::value;
+                    const float q = fminf(a[ch], b[ch]);
+                    const float D = transport_cost<PMODE>(pa[ch], pb[ch], args.p);
+                    float dq = q - qprev[ch];
                     dq = (q > thr) ? 0.0f : dq;
-                    acc = fmaf(dq, D, acc);
-                    qprev = q;
-                    advance_fwd<POS4>(a, pa, b, pb, adrA, adrB);
+                    acc[ch] = fmaf(dq, D, acc[ch]);
+                    qprev[ch] = q;
+                    advance_fwd<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch]);
+                };
+                int s = 0;
+                if constexpr (NCH == 2) {
+#pragma unroll 2
+                    for (; s < cnt[1]; ++s) {
+                        fstep(IC<0>{});
+                        fstep(IC<1>{});
+                    }
                 }
+#pragma unroll 4
+                for (; s < cnt[0]; ++s) fstep(IC<0>{});
             }
         } else if constexpr (OUT == OUT_GRAD) {
             // ---- stage 3b (gradient): walk + dL/dCDF -----------------------------------------------------
@@ -502,68 +540,88 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
             // when the next slot is known.  (It cannot overwrite the consumed CDF entry or its position:
             // a slower thread may still load that entry as the head that ends its own range.)
             if (finite) {
-                float md_prev;
-                bool inherited;  // the open group started before my range: its m*d is not known yet
-                {
-                    const float q = fminf(a, b);
-                    const float D = transport_cost<PMODE>(pa, pb, args.p);
+                float md_prev[NCH];
+                bool inherited[NCH];  // the open group started before my chunk: its m*d is not known yet
+                uint32_t consumed[NCH], fix[NCH];
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const float q = fminf(a[ch], b[ch]);
+                    const float D = transport_cost<PMODE>(pa[ch], pb[ch], args.p);
                     const float fm = (q > thr) ? 0.0f : D;
-                    // what my left neighbour needs to close ITS last slot: my first value and the m*d my
-                    // first slot has if it opens a group (idle thread: the end marker)
-                    sts64(mbox + 8u * tid, cnt > 0 ? q : f_inf(), cnt > 0 ? fm : 0.0f);
-                    inherited = (k0 > 0) && (q == qprev);
-                    md_prev = inherited ? 0.0f : fm;
-                    float dq = q - qprev;
+                    // what the chunk on my left needs to close ITS last slot: my first value and the m*d my
+                    // first slot has if it opens a group (empty chunk: the end marker)
+                    sts64(mbox + 8u * (NCH * tid + ch), cnt[ch] > 0 ? q : f_inf(), cnt[ch] > 0 ? fm : 0.0f);
+                    inherited[ch] = (k0[ch] > 0) && (q == qprev[ch]);
+                    md_prev[ch] = inherited[ch] ? 0.0f : fm;
+                    float dq = q - qprev[ch];
                     dq = (q > thr) ? 0.0f : dq;
-                    if (cnt > 0) {
-                        acc = fmaf(dq, D, acc);
-                        qprev = q;
+                    if (cnt[ch] > 0) {
+                        acc[ch] = fmaf(dq, D, acc[ch]);
+                        qprev[ch] = q;
                     }
+                    consumed[ch] = 0;
+                    fix[ch] = NO_FIX;
                 }
                 cta_sync<TPF>();  // mailbox complete (and: every raw bin was read long ago, rows 4/5 are free)
-                uint32_t consumed = 0, fix = NO_FIX;
-                if (cnt > 0) advance<POS4>(a, pa, b, pb, adrA, adrB, consumed);
-                auto step = [&]() {
-                    const float q = fminf(a, b);
-                    const float D = transport_cost<PMODE>(pa, pb, args.p);
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch)
+                    if (cnt[ch] > 0) advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
+                auto gstep = [&](auto CH) {
+                    constexpr int ch = decltype(CH)::value;
+                    const float q = fminf(a[ch], b[ch]);
+                    const float D = transport_cost<PMODE>(pa[ch], pb[ch], args.p);
                     const bool over = q > thr;
-                    float dq = q - qprev;
+                    float dq = q - qprev[ch];
                     dq = over ? 0.0f : dq;
-                    acc = fmaf(dq, D, acc);
-                    const bool same = (q == qprev);
-                    const float md = same ? md_prev : (over ? 0.0f : D);
-                    sts32o<LY::G_OFF>(consumed, md_prev - md);  // dL/dCDF of the previous slot (0 inside a group)
-                    fix = (inherited && !same) ? consumed : fix;
-                    inherited = inherited && same;
-                    md_prev = md;
-                    qprev = q;
-                    advance<POS4>(a, pa, b, pb, adrA, adrB, consumed);
+                    acc[ch] = fmaf(dq, D, acc[ch]);
+                    const bool same = (q == qprev[ch]);
+                    const float md = same ? md_prev[ch] : (over ? 0.0f : D);
+                    sts32o<LY::G_OFF>(consumed[ch], md_prev[ch] - md);  // dL/dCDF of the previous slot (0 inside a group)
+                    fix[ch] = (inherited[ch] && !same) ? consumed[ch] : fix[ch];
+                    inherited[ch] = inherited[ch] && same;
+                    md_prev[ch] = md;
+                    qprev[ch] = q;
+                    advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
                 };
-#pragma unroll 4
-                for (int s = 1; s < cnt; ++s) step();
-                float carry_out = -1.0f;  // -1 = "my whole range continues a group opened before me"
-                if (cnt > 0) {
-                    // the slot after my range: first slot of the next thread, or the end marker
-                    float qn, mdn;
-                    lds64(mbox + 8u * (tid + 1), qn, mdn);
-                    const bool same = (qn == qprev);
-                    const float md = same ? md_prev : mdn;
-                    sts32o<LY::G_OFF>(consumed, md_prev - md);
-                    fix = (inherited && !same) ? consumed : fix;
-                    inherited = inherited && same;
-                    carry_out = inherited ? -1.0f : md_prev;
-                }
-                // look-back: add the m*d of a tie group that was opened by an earlier thread
-                sts32(carry + 4u * tid, carry_out);
-                cta_sync<TPF>();
-                if (fix != NO_FIX) {
-                    uint32_t s = carry + 4u * (tid - 1);
-                    float c = lds32(s);
-                    while (c < 0.0f) {  // thread 0 never carries the marker
-                        s -= 4;
-                        c = lds32(s);
+                int s = 1;
+                if constexpr (NCH == 2) {
+#pragma unroll 2
+                    for (; s < cnt[1]; ++s) {
+                        gstep(IC<0>{});
+                        gstep(IC<1>{});
                     }
-                    sts32o<LY::G_OFF>(fix, lds32o<LY::G_OFF>(fix) + c);
+                }
+#pragma unroll 4
+                for (; s < cnt[0]; ++s) gstep(IC<0>{});
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    float carry_out = -1.0f;  // -1 = "my whole chunk continues a group opened before it"
+                    if (cnt[ch] > 0) {
+                        // the slot after my chunk: first slot of the next chunk, or the end marker
+                        float qn, mdn;
+                        lds64(mbox + 8u * (NCH * tid + ch + 1), qn, mdn);
+                        const bool same = (qn == qprev[ch]);
+                        const float md = same ? md_prev[ch] : mdn;
+                        sts32o<LY::G_OFF>(consumed[ch], md_prev[ch] - md);
+                        fix[ch] = (inherited[ch] && !same) ? consumed[ch] : fix[ch];
+                        inherited[ch] = inherited[ch] && same;
+                        carry_out = inherited[ch] ? -1.0f : md_prev[ch];
+                    }
+                    sts32(carry + 4u * (NCH * tid + ch), carry_out);
+                }
+                // look-back: add the m*d of a tie group that was opened by an earlier chunk
+                cta_sync<TPF>();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (fix[ch] != NO_FIX) {
+                        uint32_t sa = carry + 4u * (NCH * tid + ch - 1);
+                        float c = lds32(sa);
+                        while (c < 0.0f) {  // chunk 0 never carries the marker
+                            sa -= 4;
+                            c = lds32(sa);
+                        }
+                        sts32o<LY::G_OFF>(fix[ch], lds32o<LY::G_OFF>(fix[ch]) + c);
+                    }
                 }
                 cta_sync<TPF>();
             }
@@ -573,46 +631,55 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
             // (#{cu < q}, #{cv < q}) -- what `searchsorted(cu, qs)` / `searchsorted(cv, qs)` return
             // (losses.py:219).
             if (finite) {
-                int i = i0, j = k0 - i0, is = 0, js = 0, n_inherited = 0;
-                bool inherited = (k0 != 0);
-                for (int s = 0; s < cnt; ++s) {
-                    const float q = fminf(a, b);
-                    const bool take_v = b < a;
-                    if (q != qprev) {
-                        is = i;
-                        js = j;
-                        inherited = false;
+                int n_inherited[NCH];
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    int i = i0[ch], j = k0[ch] - i0[ch], is = 0, js = 0;
+                    bool inherited = (k0[ch] != 0);
+                    n_inherited[ch] = 0;
+                    for (int s = 0; s < cnt[ch]; ++s) {
+                        const float q = fminf(a[ch], b[ch]);
+                        const bool take_v = b[ch] < a[ch];
+                        if (q != qprev[ch]) {
+                            is = i;
+                            js = j;
+                            inherited = false;
+                        }
+                        if (inherited) ++n_inherited[ch];
+                        const long long o = frame * K + k0[ch] + s;
+                        if (args.plan_qs != nullptr) args.plan_qs[o] = q;
+                        if (args.plan_iu != nullptr) args.plan_iu[o] = is;
+                        if (args.plan_iv != nullptr) args.plan_iv[o] = js;
+                        if (args.plan_uq != nullptr) args.plan_uq[o] = lds32(A0 + LY::POS_OFF + 4u * is);
+                        if (args.plan_vq != nullptr) args.plan_vq[o] = lds32(B0 + LY::POS_OFF + 4u * js);
+                        float dq = q - qprev[ch];
+                        dq = (q > thr) ? 0.0f : dq;
+                        acc[ch] = fmaf(dq, transport_cost<PMODE>(pa[ch], pb[ch], args.p), acc[ch]);
+                        qprev[ch] = q;
+                        if (take_v) ++j; else ++i;
+                        advance_fwd<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch]);
                     }
-                    if (inherited) ++n_inherited;
-                    const long long o = frame * K + k0 + s;
-                    if (args.plan_qs != nullptr) args.plan_qs[o] = q;
-                    if (args.plan_iu != nullptr) args.plan_iu[o] = is;
-                    if (args.plan_iv != nullptr) args.plan_iv[o] = js;
-                    if (args.plan_uq != nullptr) args.plan_uq[o] = lds32(A0 + LY::POS_OFF + 4u * is);
-                    if (args.plan_vq != nullptr) args.plan_vq[o] = lds32(B0 + LY::POS_OFF + 4u * js);
-                    float dq = q - qprev;
-                    dq = (q > thr) ? 0.0f : dq;
-                    acc = fmaf(dq, transport_cost<PMODE>(pa, pb, args.p), acc);
-                    qprev = q;
-                    if (take_v) ++j; else ++i;
-                    advance_fwd<POS4>(a, pa, b, pb, adrA, adrB);
+                    sts32(carry + 4u * (NCH * tid + ch),
+                          __int_as_float((cnt[ch] == 0 || inherited) ? -1 : ((is << 16) | js)));
                 }
-                sts32(carry + 4u * tid, __int_as_float((cnt == 0 || inherited) ? -1 : ((is << 16) | js)));
                 cta_sync<TPF>();
-                if (n_inherited > 0) {
-                    uint32_t s = carry + 4u * (tid - 1);
-                    int c = __float_as_int(lds32(s));
-                    while (c < 0) {
-                        s -= 4;
-                        c = __float_as_int(lds32(s));
-                    }
-                    const int is2 = c >> 16, js2 = c & 0xffff;
-                    for (int t = 0; t < n_inherited; ++t) {
-                        const long long o = frame * K + k0 + t;
-                        if (args.plan_iu != nullptr) args.plan_iu[o] = is2;
-                        if (args.plan_iv != nullptr) args.plan_iv[o] = js2;
-                        if (args.plan_uq != nullptr) args.plan_uq[o] = lds32(A0 + LY::POS_OFF + 4u * is2);
-                        if (args.plan_vq != nullptr) args.plan_vq[o] = lds32(B0 + LY::POS_OFF + 4u * js2);
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (n_inherited[ch] > 0) {
+                        uint32_t sa = carry + 4u * (NCH * tid + ch - 1);
+                        int c = __float_as_int(lds32(sa));
+                        while (c < 0) {
+                            sa -= 4;
+                            c = __float_as_int(lds32(sa));
+                        }
+                        const int is2 = c >> 16, js2 = c & 0xffff;
+                        for (int t = 0; t < n_inherited[ch]; ++t) {
+                            const long long o = frame * K + k0[ch] + t;
+                            if (args.plan_iu != nullptr) args.plan_iu[o] = is2;
+                            if (args.plan_iv != nullptr) args.plan_iv[o] = js2;
+                            if (args.plan_uq != nullptr) args.plan_uq[o] = lds32(A0 + LY::POS_OFF + 4u * is2);
+                            if (args.plan_vq != nullptr) args.plan_vq[o] = lds32(B0 + LY::POS_OFF + 4u * js2);
+                        }
                     }
                 }
                 if (args.plan_cu != nullptr)
@@ -624,7 +691,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT>::TO
 
         // ---- loss of the frame: fp32 partials, summed in fp64 ---------------------------------------
         {
-            double part = static_cast<double>(acc);
+            double part = static_cast<double>(NCH == 2 ? acc[0] + acc[NCH - 1] : acc[0]);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULL_MASK, part, off);
             if constexpr (NW > 1) {

@@ -1,5 +1,5 @@
-// Per-configuration launcher: one translation unit per (TPF, E, RS) so the configs compile in
-// parallel.  Each exposes `sot_launch_<TPF>_<E>_<RS>(request, stream)`.
+// Per-configuration launcher: one translation unit per (TPF, E, RS, NCH) so the configs compile in
+// parallel.  Each exposes `sot_launch_<TPF>_<E>_<RS>_<NCH>(request, stream)`; NCH = merge chains per thread.
 //   TPF threads per frame (= per CTA), E (odd) consecutive bins per thread, RS floats per
 //   shared-memory row; the configuration accepts rows of up to min(TPF * E, RS - 7) bins.
 #pragma once
@@ -13,10 +13,10 @@ struct LaunchRequest {
     int mode;  // MODE_SPECTRA / MODE_CDF
 };
 
-template <int TPF, int E, int RS, int PMODE, int OUT, int MODE>
+template <int TPF, int E, int RS, int NCH, int PMODE, int OUT, int MODE>
 cudaError_t launch_one(const FrameArgs& a, cudaStream_t stream) {
-    auto kernel = sot_frame_kernel<TPF, E, RS, PMODE, OUT, MODE>;
-    constexpr int smem_bytes = static_cast<int>(Layout<TPF, RS, OUT>::TOTAL);
+    auto kernel = sot_frame_kernel<TPF, E, RS, NCH, PMODE, OUT, MODE>;
+    constexpr int smem_bytes = static_cast<int>(Layout<TPF, RS, OUT, NCH>::TOTAL);
     // per instantiation (and device): opt-in shared memory size and the persistent grid size
     static int cached_grid = 0, cached_dev = -1;
     int dev = 0;
@@ -38,28 +38,28 @@ cudaError_t launch_one(const FrameArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <int TPF, int E, int RS>
+template <int TPF, int E, int RS, int NCH>
 cudaError_t launch_config(const LaunchRequest& r, cudaStream_t stream) {
     const bool p2 = (r.args.p == 2.0f);
     if (r.mode == MODE_SPECTRA) {
         if (r.out == OUT_LOSS)
-            return p2 ? launch_one<TPF, E, RS, 2, OUT_LOSS, MODE_SPECTRA>(r.args, stream)
-                      : launch_one<TPF, E, RS, 0, OUT_LOSS, MODE_SPECTRA>(r.args, stream);
+            return p2 ? launch_one<TPF, E, RS, NCH, 2, OUT_LOSS, MODE_SPECTRA>(r.args, stream)
+                      : launch_one<TPF, E, RS, NCH, 0, OUT_LOSS, MODE_SPECTRA>(r.args, stream);
         if (r.out == OUT_GRAD)
-            return p2 ? launch_one<TPF, E, RS, 2, OUT_GRAD, MODE_SPECTRA>(r.args, stream)
-                      : launch_one<TPF, E, RS, 0, OUT_GRAD, MODE_SPECTRA>(r.args, stream);
-        return launch_one<TPF, E, RS, 0, OUT_PLAN, MODE_SPECTRA>(r.args, stream);
+            return p2 ? launch_one<TPF, E, RS, NCH, 2, OUT_GRAD, MODE_SPECTRA>(r.args, stream)
+                      : launch_one<TPF, E, RS, NCH, 0, OUT_GRAD, MODE_SPECTRA>(r.args, stream);
+        return launch_one<TPF, E, RS, NCH, 0, OUT_PLAN, MODE_SPECTRA>(r.args, stream);
     }
-    if (r.out == OUT_LOSS) return launch_one<TPF, E, RS, 0, OUT_LOSS, MODE_CDF>(r.args, stream);
-    if (r.out == OUT_GRAD) return launch_one<TPF, E, RS, 0, OUT_GRAD, MODE_CDF>(r.args, stream);
-    return launch_one<TPF, E, RS, 0, OUT_PLAN, MODE_CDF>(r.args, stream);
+    if (r.out == OUT_LOSS) return launch_one<TPF, E, RS, NCH, 0, OUT_LOSS, MODE_CDF>(r.args, stream);
+    if (r.out == OUT_GRAD) return launch_one<TPF, E, RS, NCH, 0, OUT_GRAD, MODE_CDF>(r.args, stream);
+    return launch_one<TPF, E, RS, NCH, 0, OUT_PLAN, MODE_CDF>(r.args, stream);
 }
 
 }  // namespace sot
 
-#define SOT_DEFINE_CONFIG(TPF, E, RS)                                                              \
-    cudaError_t sot_launch_##TPF##_##E##_##RS(const sot::LaunchRequest& r, cudaStream_t stream) { \
-        return sot::launch_config<TPF, E, RS>(r, stream);                                          \
+#define SOT_DEFINE_CONFIG(TPF, E, RS, NCH)                                                                 \
+    cudaError_t sot_launch_##TPF##_##E##_##RS##_##NCH(const sot::LaunchRequest& r, cudaStream_t stream) { \
+        return sot::launch_config<TPF, E, RS, NCH>(r, stream);                                             \
     }
-#define SOT_DECLARE_CONFIG(TPF, E, RS) \
-    cudaError_t sot_launch_##TPF##_##E##_##RS(const sot::LaunchRequest& r, cudaStream_t stream);
+#define SOT_DECLARE_CONFIG(TPF, E, RS, NCH) \
+    cudaError_t sot_launch_##TPF##_##E##_##RS##_##NCH(const sot::LaunchRequest& r, cudaStream_t stream);

@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--workload", default="sot2048-nocut-sweep", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=65536, help="frames per GPU (weak scaling)")
     ap.add_argument("--mode", default=None, choices=["recompute", "fused"], help="backward mode (default: library default)")
-    ap.add_argument("--tuning", default=None, help="threads_per_frame,bins_per_thread kernel override")
+    ap.add_argument("--tuning", default=None, help="threads_per_frame,bins_per_thread[,chains] kernel override")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=1024, help="frames per CPU-baseline step (64 signals x 16)")

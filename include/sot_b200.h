@@ -110,9 +110,10 @@ int sot_abi_version(void);
 const char* sot_last_error(void);
 /* Largest row length (max(n_u, n_v)) the kernels accept for the given outputs. */
 int sot_max_bins(int32_t with_grad, int32_t shared_positions);
-/* Tuning override for benchmarking: threads per frame (32/64/128/256) and bins per thread
- * (odd); 0, 0 restores the built-in choice.  Returns SOT_EINVAL if that pair is not compiled in. */
-int sot_set_tuning(int32_t threads_per_frame, int32_t bins_per_thread);
+/* Tuning override for benchmarking: threads per frame (32/64/128/256), bins per thread (odd) and
+ * merge chains per thread (1/2, 0 = any); 0, 0, 0 restores the built-in choice.  Returns SOT_EINVAL
+ * if that combination is not compiled in. */
+int sot_set_tuning(int32_t threads_per_frame, int32_t bins_per_thread, int32_t chains_per_thread);
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t sot_launch_count(void);
 

@@ -47,8 +47,8 @@ def test_argument_validation_happens_before_any_launch():
     assert lib.sot_forward_device(ctypes.byref(prob), ctypes.c_void_p(16), None) == -1  # unknown flag
     prob = _capi.SotProblem(4, 60000, 60000, 16, 16, 16, 16, 0, 0, 2.0, 0)
     assert lib.sot_forward_device(ctypes.byref(prob), ctypes.c_void_p(16), None) == -2  # does not fit
-    assert lib.sot_set_tuning(48, 7) == -1
-    assert lib.sot_set_tuning(0, 0) == 0
+    assert lib.sot_set_tuning(48, 7, 0) == -1
+    assert lib.sot_set_tuning(0, 0, 0) == 0
     assert _capi.launch_count() == before
 
 

@@ -53,7 +53,7 @@ def _sorted_case(g):
 # P1: bit-exact plan from the reference's own CDFs
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", G.MODULE_CASES)
-@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17), (128, 17)])
+@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17, 1), (64, 17, 2), (128, 17)])
 def test_p1_plan_from_reference_cdfs_bit_exact(capi, name, tuning):
     g = G.load(name)
     F = g["x"].shape[-1]
@@ -66,7 +66,7 @@ def test_p1_plan_from_reference_cdfs_bit_exact(capi, name, tuning):
         uq, vq, qs, _, _, iu, iv = capi.quantiles(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), 0,
                                                   from_cdf=True, want_indices=True)
     finally:
-        capi.set_tuning(0, 0)
+        capi.set_tuning(0, 0, 0)
     K = 2 * F
     assert torch.equal(qs.cpu(), g["qs"].reshape(-1, K)), "merged quantile grid"
     iu_ref = torch.searchsorted(cu, g["qs"].reshape(-1, K).contiguous())
@@ -104,7 +104,7 @@ def test_p1_unequal_supports_and_heavy_ties(capi):
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["sot512_cut", "sot512_nocut", "sot2048_cut", "sot2048_nocut", "sot512_logf_cut"])
 @pytest.mark.parametrize("p", [1.0, 2.0, 3.0])
-@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17)])
+@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17, 1), (64, 17, 2), (128, 9)])
 def test_p2_loss_and_cdf_gradients_from_reference_cdfs(capi, name, p, tuning):
     g = G.load(name)
     F = g["x"].shape[-1]
@@ -120,7 +120,7 @@ def test_p2_loss_and_cdf_gradients_from_reference_cdfs(capi, name, p, tuning):
         loss_only, _, _ = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p,
                                              capi.SOT_LIMIT if limit else 0, want_grads=False)
     finally:
-        capi.set_tuning(0, 0)
+        capi.set_tuning(0, 0, 0)
     assert torch.equal(loss, loss_only), "forward-only and fused kernels disagree on the loss"
     for r in range(cu.shape[0]):
         pn = pos.numpy()
@@ -254,7 +254,7 @@ def test_fused_and_recompute_modes_agree_bitwise(L):
     assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("tuning", [(128, 9), (64, 17), (32, 33), (128, 17), (256, 17), (256, 33)])
+@pytest.mark.parametrize("tuning", [(128, 9), (64, 17, 1), (64, 17, 2), (32, 33), (128, 17), (256, 17), (256, 33), (32, 9), (64, 9)])
 def test_every_kernel_configuration_gives_the_same_answer(capi, L, tuning):
     g = G.load("sot2048_nocut")
     base = None
@@ -267,7 +267,7 @@ def test_every_kernel_configuration_gives_the_same_answer(capi, L, tuning):
             v = mod(x, y, x_pos=g["pos_x"].to(DEV), y_pos=g["pos_y"].to(DEV))
             v.backward()
         finally:
-            capi.set_tuning(0, 0)
+            capi.set_tuning(0, 0, 0)
         cur = (v.item(), x.grad.clone(), y.grad.clone())
         if base is None:
             base = cur
