@@ -49,6 +49,7 @@ SIGNATURES = {
     "sot_plan_from_cdf_device": (ctypes.c_int, [_P, _V, _V, _V, _V, _V, _V]),
     "sot_loss_from_cdf_device": (ctypes.c_int, [_P, _V, _V, _V, _V]),
     "sot_loss_grad_host": (ctypes.c_int, [_P, _V, _V, _V, _V, ctypes.c_int32]),
+    "sot_host_release": (ctypes.c_int, [ctypes.c_int32]),
     "sot_abi_version": (ctypes.c_int, []),
     "sot_last_error": (ctypes.c_char_p, []),
     "sot_max_bins": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32]),

@@ -292,127 +292,187 @@ int sot_loss_from_cdf_device(const sot_problem* prob, float* loss, float* g_cu, 
 // ------------------------------------------------------------------------------------------
 // Host-buffer pipeline: frames are cut into chunks; chunk c+1's host->device copy, chunk c's
 // kernel and chunk c-1's device->host copy overlap on three streams (PCIe is full duplex).
+// Device buffers, streams and events live in a per-device workspace that is reused by later calls
+// (allocation would otherwise cost more than the kernels).
 // ------------------------------------------------------------------------------------------
+}  // extern "C" (reopened below)
+
+namespace {
+
+constexpr int kSlots = 3;
+constexpr int kMaxDevices = 16;
+
+struct HostSlot {
+    float *u = nullptr, *v = nullptr, *gu = nullptr, *gv = nullptr, *loss = nullptr, *up = nullptr, *pu = nullptr,
+          *pv = nullptr;
+    size_t cap_u = 0, cap_v = 0, cap_gu = 0, cap_gv = 0, cap_loss = 0, cap_up = 0, cap_pu = 0, cap_pv = 0;
+    cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+};
+struct HostWorkspace {
+    bool ready = false;
+    size_t cap_dpu = 0, cap_dpv = 0;
+    float *d_pu = nullptr, *d_pv = nullptr;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    HostSlot slot[kSlots];
+};
+HostWorkspace g_ws[kMaxDevices];
+std::mutex g_ws_mutex;
+
+cudaError_t grow(float** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return cudaSuccess;
+    if (*p != nullptr) {
+        cudaError_t e = cudaFree(*p);
+        if (e != cudaSuccess) return e;
+        *p = nullptr;
+        *cap = 0;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) *cap = bytes;
+    return e;
+}
+
+void release(HostWorkspace& w) {
+    for (int k = 0; k < kSlots; ++k) {
+        HostSlot& s = w.slot[k];
+        cudaFree(s.u);
+        cudaFree(s.v);
+        cudaFree(s.gu);
+        cudaFree(s.gv);
+        cudaFree(s.loss);
+        cudaFree(s.up);
+        cudaFree(s.pu);
+        cudaFree(s.pv);
+        if (s.in_done) cudaEventDestroy(s.in_done);
+        if (s.k_done) cudaEventDestroy(s.k_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    cudaFree(w.d_pu);
+    cudaFree(w.d_pv);
+    if (w.s_in) cudaStreamDestroy(w.s_in);
+    if (w.s_k) cudaStreamDestroy(w.s_k);
+    if (w.s_out) cudaStreamDestroy(w.s_out);
+    w = HostWorkspace();
+}
+
+}  // namespace
+
+extern "C" {
+
+int sot_host_release(int32_t device) {
+    if (device < 0 || device >= kMaxDevices) return fail(SOT_EINVAL, "bad device ordinal %d", device);
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    release(g_ws[device]);
+    return SOT_OK;
+}
+
 int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss, float* grad_u, float* grad_v,
                        int32_t device) {
     if (int rc = validate(hp)) return rc;
+    if (device < 0 || device >= kMaxDevices) return fail(SOT_EINVAL, "bad device ordinal %d", device);
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     const long long N = hp->n_frames;
     if (N == 0) return SOT_OK;
     const int n = hp->n_u, m = hp->n_v;
     const bool want_grad = grad_u != nullptr || grad_v != nullptr;
-    constexpr int kSlots = 3;
-    long long chunk = (48LL << 20) / (4LL * (n + m));  // ~48 MiB of input per chunk
+    long long chunk = (32LL << 20) / (4LL * (n + m));  // ~32 MiB of input per chunk
     chunk = (chunk / 4) * 4;
     if (chunk < 4) chunk = 4;
     if (chunk > N) chunk = ((N + 3) / 4) * 4;
+    const bool su = hp->pos_u_stride == 0, sv = hp->pos_v_stride == 0;
 
-    struct Slot {
-        float *u, *v, *gu, *gv, *loss, *up, *pu, *pv;
-        cudaEvent_t in_done, k_done, out_done;
-    } slot[kSlots];
-    memset(slot, 0, sizeof(slot));
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-    float *d_pu = nullptr, *d_pv = nullptr;
+    HostWorkspace& w = g_ws[device];
     int rc = SOT_OK;
-#define SOT_CK(call)                                 \
-    do {                                             \
-        cudaError_t _e = (call);                     \
-        if (_e != cudaSuccess && rc == SOT_OK) {     \
-            rc = cuda_fail(_e, #call);               \
-            goto done;                               \
-        }                                            \
+#define SOT_CK(call)                             \
+    do {                                         \
+        cudaError_t _e = (call);                 \
+        if (_e != cudaSuccess && rc == SOT_OK) { \
+            rc = cuda_fail(_e, #call);           \
+            goto done;                           \
+        }                                        \
     } while (0)
     {
-        SOT_CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        SOT_CK(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-        SOT_CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        const bool su = hp->pos_u_stride == 0, sv = hp->pos_v_stride == 0;
+        if (!w.ready) {
+            SOT_CK(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
+            SOT_CK(cudaStreamCreateWithFlags(&w.s_k, cudaStreamNonBlocking));
+            SOT_CK(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+            for (int k = 0; k < kSlots; ++k) {
+                SOT_CK(cudaEventCreateWithFlags(&w.slot[k].in_done, cudaEventDisableTiming));
+                SOT_CK(cudaEventCreateWithFlags(&w.slot[k].k_done, cudaEventDisableTiming));
+                SOT_CK(cudaEventCreateWithFlags(&w.slot[k].out_done, cudaEventDisableTiming));
+            }
+            w.ready = true;
+        }
         if (su) {
-            SOT_CK(cudaMalloc(&d_pu, 4LL * n));
-            SOT_CK(cudaMemcpyAsync(d_pu, hp->pos_u, 4LL * n, cudaMemcpyHostToDevice, s_in));
+            SOT_CK(grow(&w.d_pu, &w.cap_dpu, 4ULL * n));
+            SOT_CK(cudaMemcpyAsync(w.d_pu, hp->pos_u, 4ULL * n, cudaMemcpyHostToDevice, w.s_in));
         }
         if (sv) {
-            SOT_CK(cudaMalloc(&d_pv, 4LL * m));
-            SOT_CK(cudaMemcpyAsync(d_pv, hp->pos_v, 4LL * m, cudaMemcpyHostToDevice, s_in));
+            SOT_CK(grow(&w.d_pv, &w.cap_dpv, 4ULL * m));
+            SOT_CK(cudaMemcpyAsync(w.d_pv, hp->pos_v, 4ULL * m, cudaMemcpyHostToDevice, w.s_in));
         }
         for (int k = 0; k < kSlots; ++k) {
-            SOT_CK(cudaMalloc(&slot[k].u, 4LL * chunk * n));
-            SOT_CK(cudaMalloc(&slot[k].v, 4LL * chunk * m));
-            SOT_CK(cudaMalloc(&slot[k].loss, 4LL * chunk));
-            if (upstream != nullptr) SOT_CK(cudaMalloc(&slot[k].up, 4LL * chunk));
-            if (grad_u != nullptr) SOT_CK(cudaMalloc(&slot[k].gu, 4LL * chunk * n));
-            if (grad_v != nullptr) SOT_CK(cudaMalloc(&slot[k].gv, 4LL * chunk * m));
-            if (!su) SOT_CK(cudaMalloc(&slot[k].pu, 4LL * chunk * n));
-            if (!sv) SOT_CK(cudaMalloc(&slot[k].pv, 4LL * chunk * m));
-            SOT_CK(cudaEventCreateWithFlags(&slot[k].in_done, cudaEventDisableTiming));
-            SOT_CK(cudaEventCreateWithFlags(&slot[k].k_done, cudaEventDisableTiming));
-            SOT_CK(cudaEventCreateWithFlags(&slot[k].out_done, cudaEventDisableTiming));
+            HostSlot& s = w.slot[k];
+            SOT_CK(grow(&s.u, &s.cap_u, 4ULL * chunk * n));
+            SOT_CK(grow(&s.v, &s.cap_v, 4ULL * chunk * m));
+            SOT_CK(grow(&s.loss, &s.cap_loss, 4ULL * chunk));
+            if (upstream != nullptr) SOT_CK(grow(&s.up, &s.cap_up, 4ULL * chunk));
+            if (grad_u != nullptr) SOT_CK(grow(&s.gu, &s.cap_gu, 4ULL * chunk * n));
+            if (grad_v != nullptr) SOT_CK(grow(&s.gv, &s.cap_gv, 4ULL * chunk * m));
+            if (!su) SOT_CK(grow(&s.pu, &s.cap_pu, 4ULL * chunk * n));
+            if (!sv) SOT_CK(grow(&s.pv, &s.cap_pv, 4ULL * chunk * m));
         }
         long long c = 0;
         for (long long f0 = 0; f0 < N; f0 += chunk, ++c) {
-            Slot& s = slot[c % kSlots];
+            HostSlot& s = w.slot[c % kSlots];
             const long long nf = (N - f0 < chunk) ? (N - f0) : chunk;
-            if (c >= kSlots) SOT_CK(cudaStreamWaitEvent(s_in, s.out_done, 0));  // slot drained
-            SOT_CK(cudaMemcpyAsync(s.u, hp->u + f0 * n, 4LL * nf * n, cudaMemcpyHostToDevice, s_in));
-            SOT_CK(cudaMemcpyAsync(s.v, hp->v + f0 * m, 4LL * nf * m, cudaMemcpyHostToDevice, s_in));
+            if (c >= kSlots) SOT_CK(cudaStreamWaitEvent(w.s_in, s.out_done, 0));  // slot drained
+            SOT_CK(cudaMemcpyAsync(s.u, hp->u + f0 * n, 4ULL * nf * n, cudaMemcpyHostToDevice, w.s_in));
+            SOT_CK(cudaMemcpyAsync(s.v, hp->v + f0 * m, 4ULL * nf * m, cudaMemcpyHostToDevice, w.s_in));
             if (upstream != nullptr)
-                SOT_CK(cudaMemcpyAsync(s.up, upstream + f0, 4LL * nf, cudaMemcpyHostToDevice, s_in));
+                SOT_CK(cudaMemcpyAsync(s.up, upstream + f0, 4ULL * nf, cudaMemcpyHostToDevice, w.s_in));
             if (!su)
-                SOT_CK(cudaMemcpy2DAsync(s.pu, 4LL * n, hp->pos_u + f0 * hp->pos_u_stride, 4LL * hp->pos_u_stride,
-                                         4LL * n, nf, cudaMemcpyHostToDevice, s_in));
+                SOT_CK(cudaMemcpy2DAsync(s.pu, 4ULL * n, hp->pos_u + f0 * hp->pos_u_stride, 4ULL * hp->pos_u_stride,
+                                         4ULL * n, nf, cudaMemcpyHostToDevice, w.s_in));
             if (!sv)
-                SOT_CK(cudaMemcpy2DAsync(s.pv, 4LL * m, hp->pos_v + f0 * hp->pos_v_stride, 4LL * hp->pos_v_stride,
-                                         4LL * m, nf, cudaMemcpyHostToDevice, s_in));
-            SOT_CK(cudaEventRecord(s.in_done, s_in));
-            SOT_CK(cudaStreamWaitEvent(s_k, s.in_done, 0));
+                SOT_CK(cudaMemcpy2DAsync(s.pv, 4ULL * m, hp->pos_v + f0 * hp->pos_v_stride, 4ULL * hp->pos_v_stride,
+                                         4ULL * m, nf, cudaMemcpyHostToDevice, w.s_in));
+            SOT_CK(cudaEventRecord(s.in_done, w.s_in));
+            SOT_CK(cudaStreamWaitEvent(w.s_k, s.in_done, 0));
             sot_problem dp = *hp;
             dp.n_frames = nf;
             dp.u = s.u;
             dp.v = s.v;
-            dp.pos_u = su ? d_pu : s.pu;
-            dp.pos_v = sv ? d_pv : s.pv;
+            dp.pos_u = su ? w.d_pu : s.pu;
+            dp.pos_v = sv ? w.d_pv : s.pv;
             dp.pos_u_stride = su ? 0 : n;
             dp.pos_v_stride = sv ? 0 : m;
-            int krc = want_grad ? sot_forward_backward_device(&dp, s.up, s.loss, s.gu, s.gv, s_k)
-                                : sot_forward_device(&dp, s.loss, s_k);
+            const int krc = want_grad ? sot_forward_backward_device(&dp, upstream != nullptr ? s.up : nullptr, s.loss,
+                                                                    grad_u != nullptr ? s.gu : nullptr,
+                                                                    grad_v != nullptr ? s.gv : nullptr, w.s_k)
+                                      : sot_forward_device(&dp, s.loss, w.s_k);
             if (krc != SOT_OK) {
                 rc = krc;
                 goto done;
             }
-            SOT_CK(cudaEventRecord(s.k_done, s_k));
-            SOT_CK(cudaStreamWaitEvent(s_out, s.k_done, 0));
-            if (loss != nullptr) SOT_CK(cudaMemcpyAsync(loss + f0, s.loss, 4LL * nf, cudaMemcpyDeviceToHost, s_out));
+            SOT_CK(cudaEventRecord(s.k_done, w.s_k));
+            SOT_CK(cudaStreamWaitEvent(w.s_out, s.k_done, 0));
+            if (loss != nullptr) SOT_CK(cudaMemcpyAsync(loss + f0, s.loss, 4ULL * nf, cudaMemcpyDeviceToHost, w.s_out));
             if (grad_u != nullptr)
-                SOT_CK(cudaMemcpyAsync(grad_u + f0 * n, s.gu, 4LL * nf * n, cudaMemcpyDeviceToHost, s_out));
+                SOT_CK(cudaMemcpyAsync(grad_u + f0 * n, s.gu, 4ULL * nf * n, cudaMemcpyDeviceToHost, w.s_out));
             if (grad_v != nullptr)
-                SOT_CK(cudaMemcpyAsync(grad_v + f0 * m, s.gv, 4LL * nf * m, cudaMemcpyDeviceToHost, s_out));
-            SOT_CK(cudaEventRecord(s.out_done, s_out));
+                SOT_CK(cudaMemcpyAsync(grad_v + f0 * m, s.gv, 4ULL * nf * m, cudaMemcpyDeviceToHost, w.s_out));
+            SOT_CK(cudaEventRecord(s.out_done, w.s_out));
         }
-        SOT_CK(cudaStreamSynchronize(s_out));
-        SOT_CK(cudaStreamSynchronize(s_k));
-        SOT_CK(cudaStreamSynchronize(s_in));
     }
 done:
-    for (int k = 0; k < kSlots; ++k) {
-        cudaFree(slot[k].u);
-        cudaFree(slot[k].v);
-        cudaFree(slot[k].gu);
-        cudaFree(slot[k].gv);
-        cudaFree(slot[k].loss);
-        cudaFree(slot[k].up);
-        cudaFree(slot[k].pu);
-        cudaFree(slot[k].pv);
-        if (slot[k].in_done) cudaEventDestroy(slot[k].in_done);
-        if (slot[k].k_done) cudaEventDestroy(slot[k].k_done);
-        if (slot[k].out_done) cudaEventDestroy(slot[k].out_done);
-    }
-    cudaFree(d_pu);
-    cudaFree(d_pv);
-    if (s_in) cudaStreamDestroy(s_in);
-    if (s_k) cudaStreamDestroy(s_k);
-    if (s_out) cudaStreamDestroy(s_out);
+    // drain everything that was queued (also on the error path) before the host buffers are reused
+    if (w.s_out) cudaStreamSynchronize(w.s_out);
+    if (w.s_k) cudaStreamSynchronize(w.s_k);
+    if (w.s_in) cudaStreamSynchronize(w.s_in);
 #undef SOT_CK
     return rc;
 }

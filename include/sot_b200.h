@@ -101,9 +101,13 @@ int sot_loss_from_cdf_device(const sot_problem* prob, float* loss, float* g_cu, 
 /* Whole job with HOST buffers: copies u, v (and positions) to the device in chunks on two
  * streams, runs the fused kernel, copies loss and gradients back.  Blocking.  `upstream` and
  * each output are nullable host pointers.  Pinned host memory is used as-is; pageable memory
- * works but is slower.  `device` = CUDA ordinal. */
+ * works but is slower.  `device` = CUDA ordinal.  Device staging buffers are cached per device
+ * (see sot_host_release); concurrent calls are serialised. */
 int sot_loss_grad_host(const sot_problem* host_prob, const float* upstream, float* loss, float* grad_u,
                        float* grad_v, int32_t device);
+
+/* Frees the device buffers, streams and events `sot_loss_grad_host` keeps per device between calls. */
+int sot_host_release(int32_t device);
 
 /* ---- housekeeping ---------------------------------------------------------------------------- */
 int sot_abi_version(void);
