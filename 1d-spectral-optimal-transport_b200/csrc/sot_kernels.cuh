@@ -13,19 +13,21 @@
 //
 // Shared memory: rows of RS floats at COMPILE-TIME offsets, so that for a CDF entry at shared
 // address a its support position is at a + POS_OFF and its dL/dCDF at a + G_OFF (immediates):
-//   row 0 / 1 : CDF of u / v, entry [n] / [m] = +inf sentinel
-//   row 2 / 3 : support positions of u / v, entry [n] / [m] repeats the last one (the
-//               reference's clamp of the searchsorted index, losses.py:220); written once per
-//               CTA when the support is shared by all frames
-//   row 4 / 5 : (gradient kernel) dL/dCDF of u / v
-//   then      : scan scratch, first-slot mailbox + carry per thread, mbarrier
+//   rows 0, 1 : CDF of u / v, entry [n] / [m] = +inf sentinel
+//   rows 2, 3 : support positions of u / v, entry [n] / [m] repeats the last one (the reference's
+//               clamp of the searchsorted index, losses.py:220); written once per CTA when the
+//               support is shared by all frames.  (A single row for u and v when they share the
+//               grid was tried: more resident CTAs, no speed-up -- the kernel is bound by shared-
+//               memory wavefronts, not by occupancy.)
+//   rows 4, 5 : (gradient kernel) dL/dCDF of u / v
+//   then      : scan scratch, first-slot mailbox + carry per chunk, mbarrier
 // The raw rows of a frame arrive by TMA bulk copy (`cp.async.bulk`, SASS UBLKCP).  A 4*n-byte row
 // is only 4-byte aligned (n = 1025 / 257), the bulk unit is 16 bytes: the copy therefore fetches
 // the 16-byte aligned WINDOW around the row and the kernel skips the `lead` bytes in front.  The
-// landing zone is rows 0/1 (forward: each thread has its bins in registers before the CDF is
-// written in place) or rows 4/5 (gradient: free until the walk; the next frame is prefetched into
-// them as soon as stage 4 has consumed dL/dCDF).  Gradient rows leave the same way: staged in rows
-// 0/1 at the row's own 16-byte phase, bulk store of the aligned middle, <= 3 scalar stores per edge.
+// landing zone is rows 0/1: each thread has its bins in registers before the CDF is written in
+// place, and the next frame is prefetched as soon as the last reader of the CDF rows is done.
+// Gradient rows leave the same way: written over the dL/dCDF rows at the row's own 16-byte phase,
+// bulk store of the aligned middle, <= 3 scalar stores per edge.
 // Thread t owns the E consecutive bins [t*E, t*E+E) of both rows ("blocked"); E is odd so every
 // blocked access of a warp is bank-conflict free.
 #pragma once
@@ -88,9 +90,9 @@ SOT_DEVINL float f_nan() { return __int_as_float(0x7fc00000); }
 template <int TPF, int RS, int OUT, int NCH>
 struct Layout {
     static constexpr uint32_t ROW = 4u * RS;
-    static constexpr uint32_t A = 0, B = ROW;     // CDF rows (also forward landing zone / output staging)
-    static constexpr uint32_t POS_OFF = 2 * ROW;  // cdf address -> position address
-    static constexpr uint32_t G_OFF = 4 * ROW;    // cdf address -> dL/dCDF address
+    static constexpr uint32_t A = 0, B = ROW;     // CDF rows (also the landing zone of the raw rows)
+    static constexpr uint32_t POS_OFF = 2 * ROW;  // cdf address -> position address (rows 2 and 3), same for u and v
+    static constexpr uint32_t G_OFF = 4 * ROW;    // cdf address -> dL/dCDF address (rows 4 and 5; also output staging)
     static constexpr uint32_t ROWS = (OUT == OUT_GRAD) ? 6 : 4;
     static constexpr uint32_t SCRATCH = ROWS * ROW;               // 8 doubles per warp
     static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per chunk + end marker
@@ -124,42 +126,35 @@ SOT_DEVINL void sts64(uint32_t a, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
 // One merge step's advance: the consumed side (v if b < a, else u: u first on equal values, the
-// stable order of `cat(cu, cv)`) loads its next CDF entry and that entry's position and moves its
-// address; everything is predicated -- no branch, no select.  POS4 = POS_OFF + 4.
-template <uint32_t POS4>
-SOT_DEVINL void advance_fwd(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB) {
-    asm volatile(
-        "{\n"
-        ".reg .pred tv;\n"
-        "setp.lt.f32 tv, %2, %0;\n"
-        "@tv  ld.shared.f32 %2, [%5+4];\n"
-        "@tv  ld.shared.f32 %3, [%5+%6];\n"
-        "@!tv ld.shared.f32 %0, [%4+4];\n"
-        "@!tv ld.shared.f32 %1, [%4+%6];\n"
-        "@tv  add.u32 %5, %5, 4;\n"
-        "@!tv add.u32 %4, %4, 4;\n"
-        "}"
-        : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB)
-        : "n"(POS4));
-}
-// same, and returns the address of the CDF entry that was consumed
+// stable order of `cat(cu, cv)`) gets its next CDF entry and that entry's position.  ONE load per
+// array from the SELECTED address: a pair of predicated loads (one per side, half the lanes each)
+// costs a shared-memory wavefront per instruction, and wavefronts are what bounds this kernel.
+// `consumed` = address of the CDF entry that was taken.  POS4 = POS_OFF + 4.
 template <uint32_t POS4>
 SOT_DEVINL void advance(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB,
                         uint32_t& consumed) {
     asm volatile(
         "{\n"
         ".reg .pred tv;\n"
+        ".reg .f32 nv, np;\n"
         "setp.lt.f32 tv, %2, %0;\n"
         "selp.u32 %6, %5, %4, tv;\n"
-        "@tv  ld.shared.f32 %2, [%5+4];\n"
-        "@tv  ld.shared.f32 %3, [%5+%7];\n"
-        "@!tv ld.shared.f32 %0, [%4+4];\n"
-        "@!tv ld.shared.f32 %1, [%4+%7];\n"
+        "ld.shared.f32 nv, [%6+4];\n"
+        "ld.shared.f32 np, [%6+%7];\n"
         "@tv  add.u32 %5, %5, 4;\n"
         "@!tv add.u32 %4, %4, 4;\n"
+        "selp.f32 %2, nv, %2, tv;\n"
+        "selp.f32 %3, np, %3, tv;\n"
+        "selp.f32 %0, %0, nv, tv;\n"
+        "selp.f32 %1, %1, np, tv;\n"
         "}"
-        : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB), "=r"(consumed)
+        : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB), "=&r"(consumed)
         : "n"(POS4));
+}
+template <uint32_t POS4>
+SOT_DEVINL void advance_fwd(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB) {
+    uint32_t consumed;
+    advance<POS4>(a, pa, b, pb, adrA, adrB, consumed);
 }
 
 // fp64 reciprocal of a positive float >= 1e-7: hardware approximation + two Newton steps
@@ -262,7 +257,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     constexpr int SEARCH_TOP = 1 << (ilog2_ceil(TPF * E + 1) - 1);
     constexpr uint32_t NO_FIX = 0xffffffffu;
     constexpr uint32_t POS4 = LY::POS_OFF + 4;
-    constexpr uint32_t LAND = WITH_GRAD ? LY::G_OFF : LY::A;  // landing zone rows (u, then v at + ROW)
+    constexpr uint32_t LAND = LY::A;  // landing zone rows (u, then v at + ROW)
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int n = args.n, m = args.m, K = n + m;
@@ -356,8 +351,8 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             for (int idx = tid; idx <= m; idx += TPF) fsm[3 * RS + idx] = gpv[min(idx, m - 1)];
         }
         if constexpr (WITH_GRAD) {
-            // the previous frame's output store must have finished READING its staging rows (rows 0/1)
-            // before this frame's CDFs are written there
+            // the previous frame's output store must have finished READING its staging rows (the dL/dCDF
+            // rows) before this frame's walk writes them again
             if (tid == 0) bulk_wait_read_all();
         }
 
@@ -562,7 +557,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     consumed[ch] = 0;
                     fix[ch] = NO_FIX;
                 }
-                cta_sync<TPF>();  // mailbox complete (and: every raw bin was read long ago, rows 4/5 are free)
+                cta_sync<TPF>();  // mailbox complete
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch)
                     if (cnt[ch] > 0) advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
@@ -710,9 +705,15 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             // the landing zone (CDF rows) is free: fetch the next frame
             if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
         } else {
-            float og_u[E], og_v[E];  // finished gradient values of my bins
+            // ---- stages 4 + 5: gradient rows, written over the dL/dCDF rows at the phase (address mod 16)
+            // of their destination so that the aligned middle can leave by bulk store --------------------
+            float* const ou = args.grad_u != nullptr ? args.grad_u + frame * n : nullptr;
+            float* const ov = args.grad_v != nullptr ? args.grad_v + frame * m : nullptr;
+            const uint32_t lead_u = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ou) & 15);
+            const uint32_t lead_v = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ov) & 15);
+            const uint32_t GA0 = A0 + LY::G_OFF, GB0 = B0 + LY::G_OFF;
             if constexpr (MODE == MODE_SPECTRA) {
-                // ---- stage 4: cumsum transpose (suffix sums of dL/dCDF) and the normalisation chain rule.
+                // cumsum transpose (suffix sums of dL/dCDF) and the normalisation chain rule.
                 // sum_i gw_i w_i = sum_i (dL/dc_i) c_i (Abel summation), so the mass term needs only the
                 // CDF values and dL/dCDF that are already in shared memory.
                 float lsu[E], lsv[E];
@@ -720,13 +721,13 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
 #pragma unroll
                 for (int c = E - 1; c >= 0; --c) {
                     if (in_u || e0 + c < n) {
-                        const float gq = lds32(A0 + LY::G_OFF + 4 * (e0 + c));
+                        const float gq = lds32(GA0 + 4 * (e0 + c));
                         su += gq;
                         du = fmaf(gq, lds32(A0 + 4 * (e0 + c)), du);
                     }
                     lsu[c] = su;
                     if (in_v || e0 + c < m) {
-                        const float gq = lds32(B0 + LY::G_OFF + 4 * (e0 + c));
+                        const float gq = lds32(GB0 + 4 * (e0 + c));
                         sv += gq;
                         dv = fmaf(gq, lds32(B0 + 4 * (e0 + c)), dv);
                     }
@@ -754,15 +755,20 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                         dot_u += scratch[6 * NW + k];
                         dot_v += scratch[7 * NW + k];
                     }
+                } else {
+                    __syncwarp();
                 }
+                // every thread has read its CDF and dL/dCDF entries (barriers above): the CDF rows can take
+                // the next frame, the dL/dCDF rows the finished gradients
+                if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
                 // a clamped mass has no derivative (torch.where picks the constant branch)
                 const double corr_u = u_live ? (cut_scale ? dot_u + dot_v : dot_u) : 0.0;
                 const double corr_v = (!cut_scale && v_live) ? dot_v : 0.0;
                 // gw = offset + local suffix; (offset - corr) is formed in fp64 before rounding
                 const float bu = static_cast<float>(off_u - corr_u), bv = static_cast<float>(off_v - corr_v);
                 const float up = args.upstream != nullptr ? args.upstream[frame] : 1.0f;
-                const float ku = static_cast<float>(inv_u) * up * (square ? 2.0f : 1.0f);
-                const float kv = static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f);
+                const float ku = finite ? static_cast<float>(inv_u) * up * (square ? 2.0f : 1.0f) : f_nan();
+                const float kv = finite ? static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f) : f_nan();
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
                     float ga = (bu + lsu[c]) * ku;
@@ -771,31 +777,26 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                         ga *= xu[c];
                         gb *= xv[c];
                     }
-                    og_u[c] = finite ? ga : f_nan();
-                    og_v[c] = finite ? gb : f_nan();
+                    if (in_u || e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), ga);
+                    if (in_v || e0 + c < m) sts32(GB0 + lead_v + 4 * (e0 + c), gb);
                 }
             } else {
+                // parity harness: the rows ARE dL/dCDF, only shifted to the destination's phase
+                float og_u[E], og_v[E];
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    og_u[c] = (e0 + c < n) ? lds32(A0 + LY::G_OFF + 4 * (e0 + c)) : 0.0f;
-                    og_v[c] = (e0 + c < m) ? lds32(B0 + LY::G_OFF + 4 * (e0 + c)) : 0.0f;
+                    og_u[c] = (e0 + c < n) ? lds32(GA0 + 4 * (e0 + c)) : 0.0f;
+                    og_v[c] = (e0 + c < m) ? lds32(GB0 + 4 * (e0 + c)) : 0.0f;
+                }
+                cta_sync<TPF>();
+                if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
+#pragma unroll
+                for (int c = 0; c < E; ++c) {
+                    if (e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), og_u[c]);
+                    if (e0 + c < m) sts32(GB0 + lead_v + 4 * (e0 + c), og_v[c]);
                 }
             }
-
-            // ---- stage 5: stage the two gradient rows at their own 16-byte phase and store them ---------
-            float* const ou = args.grad_u != nullptr ? args.grad_u + frame * n : nullptr;
-            float* const ov = args.grad_v != nullptr ? args.grad_v + frame * m : nullptr;
-            const uint32_t lead_u = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ou) & 15);
-            const uint32_t lead_v = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ov) & 15);
-            fence_async_smem();  // order my generic-proxy accesses before the TMA traffic that follows
-            cta_sync<TPF>();     // every thread is done with the CDF rows and with dL/dCDF
-            if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);  // rows 4/5 are free
-#pragma unroll
-            for (int c = 0; c < E; ++c) {
-                if (in_u || e0 + c < n) sts32(A0 + lead_u + 4 * (e0 + c), og_u[c]);
-                if (in_v || e0 + c < m) sts32(B0 + lead_v + 4 * (e0 + c), og_v[c]);
-            }
-            fence_async_smem();
+            fence_async_smem();  // my generic-proxy writes, before the bulk store reads them
             cta_sync<TPF>();
             // aligned middle by bulk store, the (< 4)-float edges by plain stores
             {
@@ -804,21 +805,21 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 const uint32_t body_u = (4u * n - head_u) & ~15u, body_v = (4u * m - head_v) & ~15u;
                 if (tid == 0) {
                     if (ou != nullptr && body_u > 0)
-                        bulk_s2g(reinterpret_cast<char*>(ou) + head_u, smem + LY::A + lead_u + head_u, body_u);
+                        bulk_s2g(reinterpret_cast<char*>(ou) + head_u, smem + LY::A + LY::G_OFF + lead_u + head_u, body_u);
                     if (ov != nullptr && body_v > 0)
-                        bulk_s2g(reinterpret_cast<char*>(ov) + head_v, smem + LY::B + lead_v + head_v, body_v);
+                        bulk_s2g(reinterpret_cast<char*>(ov) + head_v, smem + LY::B + LY::G_OFF + lead_v + head_v, body_v);
                     bulk_commit();
                 }
                 if (tid < 8 && ou != nullptr) {  // threads 0-3: head floats, 4-7: tail floats
                     const int hf = static_cast<int>(head_u >> 2), tf = n - hf - static_cast<int>(body_u >> 2);
                     const int idx = tid < 4 ? tid : n - tf + (tid - 4);
-                    if (tid < 4 ? (tid < hf) : (tid - 4 < tf)) ou[idx] = lds32(A0 + lead_u + 4u * idx);
+                    if (tid < 4 ? (tid < hf) : (tid - 4 < tf)) ou[idx] = lds32(GA0 + lead_u + 4u * idx);
                 }
                 if (tid >= 8 && tid < 16 && ov != nullptr) {
                     const int t8 = tid - 8;
                     const int hf = static_cast<int>(head_v >> 2), tf = m - hf - static_cast<int>(body_v >> 2);
                     const int idx = t8 < 4 ? t8 : m - tf + (t8 - 4);
-                    if (t8 < 4 ? (t8 < hf) : (t8 - 4 < tf)) ov[idx] = lds32(B0 + lead_v + 4u * idx);
+                    if (t8 < 4 ? (t8 < hf) : (t8 - 4 < tf)) ov[idx] = lds32(GB0 + lead_v + 4u * idx);
                 }
             }
         }
