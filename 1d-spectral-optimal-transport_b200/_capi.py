@@ -13,7 +13,7 @@ import torch
 
 from . import build as _build
 
-SOT_SQUARE, SOT_CUT_SCALE, SOT_LIMIT, SOT_RAW_WEIGHTS = 1, 2, 4, 8
+SOT_SQUARE, SOT_CUT_SCALE, SOT_LIMIT, SOT_RAW_WEIGHTS, SOT_UNIFORM_GRID = 1, 2, 4, 8, 16
 ABI_VERSION = 1
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers

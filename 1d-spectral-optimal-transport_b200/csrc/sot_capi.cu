@@ -135,7 +135,7 @@ int validate(const sot_problem* p) {
     if (p->pos_u_stride < 0 || p->pos_v_stride < 0) return fail(SOT_EINVAL, "negative position stride");
     if (!(p->p >= 1.0f))  // also rejects NaN; losses.py:271
         return fail(SOT_EDOMAIN, "The OT loss is only valid for p>=1, %g was given", (double)p->p);
-    if (p->flags & ~(SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS))
+    if (p->flags & ~(SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS | SOT_UNIFORM_GRID))
         return fail(SOT_EINVAL, "unknown flag bits");
     if ((p->n_frames + 3) / 4 > 0x7fffffffLL) return fail(SOT_ETOOBIG, "too many frames for one launch");
     return SOT_OK;

@@ -183,8 +183,15 @@ SOT_DEVINL int merge_path(const float* __restrict__ A, const float* __restrict__
 // |d|^p; PMODE 2 -> d*d compiled in (losses.py:313 with p=2); PMODE 0 -> any p at run time:
 // d*d for 2, |d| for 1 (:311-312), powf(|d|, p) otherwise (:313)
 template <int PMODE>
+SOT_DEVINL float cost_of_gap(float d, float p);
+
+template <int PMODE>
 SOT_DEVINL float transport_cost(float pa, float pb, float p) {
-    const float d = pa - pb;
+    return cost_of_gap<PMODE>(pa - pb, p);
+}
+
+template <int PMODE>
+SOT_DEVINL float cost_of_gap(float d, float p) {
     // __fmul_rn: never contracted into an FMA with a later subtraction, so |d|^2 is rounded
     // once on its own exactly like the reference's `diff.pow(2)` tensor (losses.py:313)
     if constexpr (PMODE == 2) {

@@ -19,7 +19,10 @@
 //               support is shared by all frames.  (A single row for u and v when they share the
 //               grid was tried: more resident CTAs, no speed-up -- the kernel is bound by shared-
 //               memory wavefronts, not by occupancy.)
-//   rows 4, 5 : (gradient kernel) dL/dCDF of u / v
+//               UNIFORM GRIDS (template flag UNI; every linear-frequency config): positions are
+//               pos[0] + i*h exactly, so these two rows and the position load of every merged slot
+//               disappear -- the position difference of the two heads is tracked with exact +-h steps.
+//   next 2    : (gradient kernel) dL/dCDF of u / v
 //   then      : scan scratch, first-slot mailbox + carry per chunk, mbarrier
 // The raw rows of a frame arrive by TMA bulk copy (`cp.async.bulk`, SASS UBLKCP).  A 4*n-byte row
 // is only 4-byte aligned (n = 1025 / 257), the bulk unit is 16 bytes: the copy therefore fetches
@@ -42,6 +45,7 @@ enum : int {
     FLAG_CUT_SCALE = 2,  // dont_normalize       losses.py:180-182
     FLAG_LIMIT = 4,      // limit_quantile_range losses.py:306-307
     FLAG_RAW = 8,        // rows are weights used as given (module-level wasserstein_1d, :223-313)
+    FLAG_UNIFORM = 16,   // caller asserts: shared supports with pos[i] = pos[0] + i*h EXACTLY in fp32
 };
 
 enum : int {
@@ -87,13 +91,14 @@ SOT_DEVINL float f_inf() { return __int_as_float(0x7f800000); }
 SOT_DEVINL float f_nan() { return __int_as_float(0x7fc00000); }
 
 // ---- compile-time shared-memory layout ---------------------------------------------------------
-template <int TPF, int RS, int OUT, int NCH>
+template <int TPF, int RS, int OUT, int NCH, bool UNI>
 struct Layout {
     static constexpr uint32_t ROW = 4u * RS;
     static constexpr uint32_t A = 0, B = ROW;     // CDF rows (also the landing zone of the raw rows)
-    static constexpr uint32_t POS_OFF = 2 * ROW;  // cdf address -> position address (rows 2 and 3), same for u and v
-    static constexpr uint32_t G_OFF = 4 * ROW;    // cdf address -> dL/dCDF address (rows 4 and 5; also output staging)
-    static constexpr uint32_t ROWS = (OUT == OUT_GRAD) ? 6 : 4;
+    static constexpr uint32_t POS_OFF = 2 * ROW;  // cdf address -> position address (two rows; none when UNI)
+    static constexpr uint32_t PROWS = UNI ? 0 : 2;
+    static constexpr uint32_t G_OFF = (2 + PROWS) * ROW;  // cdf address -> dL/dCDF address (two rows; also output staging)
+    static constexpr uint32_t ROWS = 2 + PROWS + ((OUT == OUT_GRAD) ? 2 : 0);
     static constexpr uint32_t SCRATCH = ROWS * ROW;               // 8 doubles per warp
     static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per chunk + end marker
     static constexpr uint32_t CARRY = MBOX + 8u * (NCH * TPF + 1);
@@ -151,6 +156,30 @@ SOT_DEVINL void advance(float& a, float& pa, float& b, float& pb, uint32_t& adrA
         : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB), "=&r"(consumed)
         : "n"(POS4));
 }
+// Uniform-grid advance: no position load; `d` = pos_u[head] - pos_v[head] moves by exactly +h when u
+// advances and -h when v advances -- except onto the +inf sentinel, whose position repeats the last
+// one (the reference's index clamp).
+SOT_DEVINL void advance_uni(float& a, float& d, float& b, uint32_t& adrA, uint32_t& adrB, uint32_t& consumed,
+                            float h, float neg_h) {
+    asm volatile(
+        "{\n"
+        ".reg .pred tv, live;\n"
+        ".reg .f32 nv, dh;\n"
+        "setp.lt.f32 tv, %2, %0;\n"
+        "selp.u32 %5, %4, %3, tv;\n"
+        "ld.shared.f32 nv, [%5+4];\n"
+        "@tv  add.u32 %4, %4, 4;\n"
+        "@!tv add.u32 %3, %3, 4;\n"
+        "selp.f32 dh, %7, %6, tv;\n"
+        "setp.lt.f32 live, nv, 0f7F800000;\n"
+        "selp.f32 %2, nv, %2, tv;\n"
+        "selp.f32 %0, %0, nv, tv;\n"
+        "@live add.rn.f32 %1, %1, dh;\n"
+        "}"
+        : "+f"(a), "+f"(d), "+f"(b), "+r"(adrA), "+r"(adrB), "=&r"(consumed)
+        : "f"(h), "f"(neg_h));
+}
+
 template <uint32_t POS4>
 SOT_DEVINL void advance_fwd(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB) {
     uint32_t consumed;
@@ -246,11 +275,12 @@ SOT_DEVINL bool row_is_bulk(const float* base, long long f, int width, long long
 template <int N>
 using IC = std::integral_constant<int, N>;
 
-template <int TPF, int E, int RS, int NCH, int PMODE, int OUT, int MODE>
-__global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH>::TOTAL, OUT))
+template <int TPF, int E, int RS, int NCH, bool UNI, int PMODE, int OUT, int MODE>
+__global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH, UNI>::TOTAL, OUT))
     sot_frame_kernel(const FrameArgs args) {
     static_assert(NCH == 1 || NCH == 2, "one or two merge chains per thread");
-    using LY = Layout<TPF, RS, OUT, NCH>;
+    static_assert(!(UNI && OUT == OUT_PLAN), "the plan emitter always reads positions");
+    using LY = Layout<TPF, RS, OUT, NCH, UNI>;
     constexpr int NCHUNK = NCH * TPF;
     constexpr bool WITH_GRAD = (OUT == OUT_GRAD);
     constexpr int NW = TPF / 32;
@@ -297,10 +327,18 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         fence_mbar_init();
         sts64(mbox + 8u * NCHUNK, f_inf(), 0.0f);  // virtual slot K: a new group with m*d = 0
     }
-    if (pos_shared) {  // positions once per CTA
+    float pu0 = 0.0f, pv0 = 0.0f, hstep = 0.0f;  // (UNI) pos_u[i] = pu0 + i*hstep, pos_v[j] = pv0 + j*hstep
+    if constexpr (UNI) {
+        pu0 = args.pos_u[0];
+        pv0 = args.pos_v[0];
+        hstep = args.pos_u[1] - pu0;
+    } else if (pos_shared) {  // positions once per CTA
         for (int idx = tid; idx <= n; idx += TPF) fsm[2 * RS + idx] = args.pos_u[min(idx, n - 1)];
         for (int idx = tid; idx <= m; idx += TPF) fsm[3 * RS + idx] = args.pos_v[min(idx, m - 1)];
     }
+    (void)pu0;
+    (void)pv0;
+    (void)hstep;
     __syncthreads();
 
     auto issue_load = [&](long long f, uint32_t lu, uint32_t lv) {  // one elected thread
@@ -344,7 +382,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             lead_in_v = row_lead(args.v, next, m);
             bulk_in = row_is_bulk(args.u, next, n, args.n_frames) && row_is_bulk(args.v, next, m, args.n_frames);
         }
-        if (!pos_shared) {  // per-frame supports
+        if (!UNI && !pos_shared) {  // per-frame supports
             const float* gpu = args.pos_u + frame * args.pos_u_stride;
             const float* gpv = args.pos_v + frame * args.pos_v_stride;
             for (int idx = tid; idx <= n; idx += TPF) fsm[2 * RS + idx] = gpu[min(idx, n - 1)];
@@ -493,9 +531,16 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 adrA[ch] = A0 + 4u * i0[ch];
                 adrB[ch] = B0 + 4u * (k0[ch] - i0[ch]);
                 a[ch] = lds32(adrA[ch]);
-                pa[ch] = lds32o<LY::POS_OFF>(adrA[ch]);
                 b[ch] = lds32(adrB[ch]);
-                pb[ch] = lds32o<LY::POS_OFF>(adrB[ch]);
+                if constexpr (UNI) {  // pa := position difference of the two heads (indices clamped), pb := 0
+                    const float xa = pu0 + hstep * static_cast<float>(min(i0[ch], n - 1));
+                    const float xb = pv0 + hstep * static_cast<float>(min(k0[ch] - i0[ch], m - 1));
+                    pa[ch] = xa - xb;
+                    pb[ch] = 0.0f;
+                } else {
+                    pa[ch] = lds32o<LY::POS_OFF>(adrA[ch]);
+                    pb[ch] = lds32o<LY::POS_OFF>(adrB[ch]);
+                }
                 if (k0[ch] > 0) {  // else: the zero the reference pads in front of qs (losses.py:301)
                     const float al = i0[ch] > 0 ? lds32(adrA[ch] - 4) : -f_inf();
                     const float bl = k0[ch] - i0[ch] > 0 ? lds32(adrB[ch] - 4) : -f_inf();
@@ -510,12 +555,17 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 auto fstep = [&](auto CH) {
                     constexpr int ch = decltype(CH)::value;
                     const float q = fminf(a[ch], b[ch]);
-                    const float D = transport_cost<PMODE>(pa[ch], pb[ch], args.p);
+                    const float D = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
                     float dq = q - qprev[ch];
                     dq = (q > thr) ? 0.0f : dq;
                     acc[ch] = fmaf(dq, D, acc[ch]);
                     qprev[ch] = q;
-                    advance_fwd<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch]);
+                    if constexpr (UNI) {
+                        uint32_t consumed;
+                        advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed, hstep, -hstep);
+                    } else {
+                        advance_fwd<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch]);
+                    }
                 };
                 int s = 0;
                 if constexpr (NCH == 2) {
@@ -541,7 +591,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                     const float q = fminf(a[ch], b[ch]);
-                    const float D = transport_cost<PMODE>(pa[ch], pb[ch], args.p);
+                    const float D = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
                     const float fm = (q > thr) ? 0.0f : D;
                     // what the chunk on my left needs to close ITS last slot: my first value and the m*d my
                     // first slot has if it opens a group (empty chunk: the end marker)
@@ -560,11 +610,16 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 cta_sync<TPF>();  // mailbox complete
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch)
-                    if (cnt[ch] > 0) advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
+                    if (cnt[ch] > 0) {
+                        if constexpr (UNI)
+                            advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed[ch], hstep, -hstep);
+                        else
+                            advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
+                    }
                 auto gstep = [&](auto CH) {
                     constexpr int ch = decltype(CH)::value;
                     const float q = fminf(a[ch], b[ch]);
-                    const float D = transport_cost<PMODE>(pa[ch], pb[ch], args.p);
+                    const float D = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
                     const bool over = q > thr;
                     float dq = q - qprev[ch];
                     dq = over ? 0.0f : dq;
@@ -576,7 +631,10 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     inherited[ch] = inherited[ch] && same;
                     md_prev[ch] = md;
                     qprev[ch] = q;
-                    advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
+                    if constexpr (UNI)
+                        advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed[ch], hstep, -hstep);
+                    else
+                        advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
                 };
                 int s = 1;
                 if constexpr (NCH == 2) {

@@ -137,6 +137,42 @@ def _order(pos: torch.Tensor, w: torch.Tensor, owner: torch.Tensor):
     return pos_sorted.contiguous(), torch.gather(w, 1, perm)
 
 
+_uniform_cache: dict = {}  # (id(x_pos), id(y_pos)) -> (weakref, weakref, version, version, uniform?)
+
+
+def _uniform_grid(pu: torch.Tensor, pv: torch.Tensor, owner_u: torch.Tensor, owner_v: torch.Tensor) -> bool:
+    """Are both supports EXACT uniform grids pos[i] = pos[0] + i*h with one common power-of-two h, so
+    that every position and every position difference is exact in float32?  True for rfftfreq / max
+    with a power-of-two n_fft (trainer.py:193-197) and for `fixed_x = linspace(0, 1, 2**k + 1)`
+    (losses.py:124-125).  The kernels then compute positions instead of loading them -- bit-identical
+    results, fewer shared-memory accesses.  One device->host read per distinct pair of caller tensors."""
+    if pu.ndim != 1 or pv.ndim != 1 or pu.shape[0] < 2 or pv.shape[0] < 2:
+        return False
+    key = (id(owner_u), id(owner_v))
+    hit = _uniform_cache.get(key)
+    if (hit is not None and hit[0]() is owner_u and hit[1]() is owner_v and hit[2] == owner_u._version
+            and hit[3] == owner_v._version):
+        return hit[4]
+    h = pu[1] - pu[0]
+    ok = (pu == pu[0] + torch.arange(pu.shape[0], device=pu.device) * h).all() & \
+         (pv == pv[0] + torch.arange(pv.shape[0], device=pv.device) * h).all()
+    h_val, ok_val, u0, v0 = torch.stack((h, ok.to(h.dtype), pu[0], pv[0])).tolist()  # the one sync
+    uniform = False
+    if ok_val == 1.0 and h_val > 0.0:
+        import math
+        mant, _ = math.frexp(h_val)
+        span = max(pu.shape[0], pv.shape[0]) + abs(u0 / h_val) + abs(v0 / h_val)
+        uniform = (mant == 0.5 and float(u0 / h_val).is_integer() and float(v0 / h_val).is_integer()
+                   and span < 2 ** 23)
+    try:
+        drop = lambda _, k=key: _uniform_cache.pop(k, None)  # noqa: E731
+        _uniform_cache[key] = (weakref.ref(owner_u, drop), weakref.ref(owner_v, drop), owner_u._version,
+                               owner_v._version, uniform)
+    except TypeError:
+        pass
+    return uniform
+
+
 def sot_frames(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=False, require_sort=True,
                raw_weights=False, backward_mode="recompute") -> torch.Tensor:
     """Per-frame W_p^p, shape (N,), differentiable w.r.t. x and y."""
@@ -153,7 +189,8 @@ def sot_frames(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=Fal
     if sort_v:
         pv, v = _order(pv, v, y_pos)
     flags = ((_capi.SOT_SQUARE if square else 0) | (_capi.SOT_CUT_SCALE if cut_scale else 0) |
-             (_capi.SOT_LIMIT if limit else 0) | (_capi.SOT_RAW_WEIGHTS if raw_weights else 0))
+             (_capi.SOT_LIMIT if limit else 0) | (_capi.SOT_RAW_WEIGHTS if raw_weights else 0) |
+             (_capi.SOT_UNIFORM_GRID if _uniform_grid(pu, pv, x_pos, y_pos) else 0))
     return _SotFrames.apply(u, v, pu, pv, float(p), flags, backward_mode)
 
 

@@ -209,6 +209,8 @@ def main():
 
     # ---- dominant kernel alone (fused forward+backward launch), CUDA events on its stream ----
     flags = _capi.SOT_SQUARE | (_capi.SOT_CUT_SCALE | _capi.SOT_LIMIT if cut else 0)
+    if grid == "linear":  # what the module detects for these grids (exact i * 2**-k positions)
+        flags |= _capi.SOT_UNIFORM_GRID
     up = torch.full((args.frames,), 1.0 / (args.frames * world), device=dev)
     k_ms = []
     for it in range(3 + args.steps):

@@ -34,6 +34,12 @@ extern "C" {
 #define SOT_RAW_WEIGHTS 8 /* rows are weights used as given, no normalisation: the module-level
                             `wasserstein_1d(u_values, v_values, u_weights, v_weights)` losses.py:223 */
 
+#define SOT_UNIFORM_GRID 16 /* the caller asserts: one support shared by all frames (strides 0) with
+                             pos_u[i] = pos_u[0] + i*h and pos_v[j] = pos_v[0] + j*h EXACTLY in float32,
+                             h = pos_u[1] - pos_u[0] (e.g. rfftfreq / max for power-of-two n_fft,
+                             trainer.py:193-197).  Positions are then computed, not loaded: same bits,
+                             fewer shared-memory accesses.  Ignored by sot_quantiles_device. */
+
 /* error codes */
 #define SOT_OK 0
 #define SOT_EINVAL (-1)   /* bad pointer / size / flag combination        */
@@ -53,7 +59,7 @@ typedef struct sot_problem {
     int64_t pos_u_stride;  /*   of a [N, n_*] array with this element stride                */
     int64_t pos_v_stride;
     float p;               /* order of the distance, >= 1 (result is W_p^p, no root)        */
-    int32_t flags;         /* SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS      */
+    int32_t flags;         /* SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS | SOT_UNIFORM_GRID */
 } sot_problem;
 
 /* ---- the hot path ------------------------------------------------------------------------- */

@@ -105,7 +105,8 @@ def test_p1_unequal_supports_and_heavy_ties(capi):
 @pytest.mark.parametrize("name", ["sot512_cut", "sot512_nocut", "sot2048_cut", "sot2048_nocut", "sot512_logf_cut"])
 @pytest.mark.parametrize("p", [1.0, 2.0, 3.0])
 @pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17, 1), (64, 17, 2), (128, 9)])
-def test_p2_loss_and_cdf_gradients_from_reference_cdfs(capi, name, p, tuning):
+@pytest.mark.parametrize("uniform", [False, True])
+def test_p2_loss_and_cdf_gradients_from_reference_cdfs(capi, name, p, tuning, uniform):
     g = G.load(name)
     F = g["x"].shape[-1]
     if tuning[0] * tuning[1] and tuning[0] * tuning[1] < F:
@@ -113,12 +114,14 @@ def test_p2_loss_and_cdf_gradients_from_reference_cdfs(capi, name, p, tuning):
     limit = bool(g["meta"]["ctor"].get("limit_quantile_range", False))
     cu, cv = g["cu"].reshape(-1, F).contiguous(), g["cv"].reshape(-1, F).contiguous()
     pos = g["pos_x"]
+    if uniform and g["meta"]["grid"] != "linear":
+        pytest.skip("the uniform-grid kernels need an exact linear grid")
+    flags = (capi.SOT_LIMIT if limit else 0) | (capi.SOT_UNIFORM_GRID if uniform else 0)
     capi.set_tuning(*tuning)
     try:
-        loss, g_cu, g_cv = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p,
-                                              capi.SOT_LIMIT if limit else 0)
-        loss_only, _, _ = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p,
-                                             capi.SOT_LIMIT if limit else 0, want_grads=False)
+        loss, g_cu, g_cv = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p, flags)
+        loss_only, _, _ = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p, flags,
+                                             want_grads=False)
     finally:
         capi.set_tuning(0, 0, 0)
     assert torch.equal(loss, loss_only), "forward-only and fused kernels disagree on the loss"
@@ -235,6 +238,44 @@ def test_module_forward_backward_vs_reference_fixture(capi, L, name, mode):
             if same:
                 assert abs(rows[r].item() - ref_rows[r].item()) <= 2e-6 * abs(ref_rows[r].item())
     del ref_gx, ref_gy
+
+
+@pytest.mark.parametrize("name", ["sot512_cut", "sot2048_cut", "sot2048_nocut", "sot512_p1_nosquare", "sot512_p3"])
+def test_uniform_grid_kernels_are_bit_identical_to_the_general_ones(capi, name):
+    """Positions computed as pos[0] + i*h (exact for these grids) vs positions loaded from memory."""
+    g = G.load(name)
+    kw = G.oracle_kwargs(g["meta"]["ctor"])
+    F = g["x"].shape[-1]
+    x, y = g["x"].reshape(-1, F).to(DEV), g["y"].reshape(-1, F).to(DEV)
+    pos = g["pos_x"].to(DEV)
+    flags = _flags(capi, kw)
+    up = torch.rand(x.shape[0], device=DEV)
+    a = capi.forward_backward(x, y, pos, pos, float(kw["p"]), flags, upstream=up)
+    b = capi.forward_backward(x, y, pos, pos, float(kw["p"]), flags | capi.SOT_UNIFORM_GRID, upstream=up)
+    for s, t2 in zip(a, b):
+        assert torch.equal(s, t2)
+    assert torch.equal(capi.forward(x, y, pos, pos, float(kw["p"]), flags),
+                       capi.forward(x, y, pos, pos, float(kw["p"]), flags | capi.SOT_UNIFORM_GRID))
+    # different lengths and offsets on the two sides: pos_v = 0.25 + j*h on 200 bins vs pos_u on F bins
+    h = (pos[1] - pos[0]).item()
+    pv = 0.25 + torch.arange(200, device=DEV) * h
+    yv = y[:, :200].contiguous()
+    a = capi.forward_backward(x, yv, pos, pv, float(kw["p"]), flags)
+    b = capi.forward_backward(x, yv, pos, pv, float(kw["p"]), flags | capi.SOT_UNIFORM_GRID)
+    for s, t2 in zip(a, b):
+        assert torch.equal(s, t2)
+
+
+def test_module_detects_uniform_grids(L):
+    from sot_b200 import synthetic as S
+    lin = S.linear_positions(2048).to(DEV)
+    assert L._uniform_grid(lin, lin.clone(), lin, lin)
+    fx = torch.linspace(0, 1, 257, device=DEV)
+    assert L._uniform_grid(fx, fx, fx, fx)
+    logf = S.logf_positions(512).to(DEV)
+    assert not L._uniform_grid(logf, logf, logf, logf)
+    odd = torch.linspace(0, 1, 1000, device=DEV)  # step 1/999: not exact in binary
+    assert not L._uniform_grid(odd, odd, odd, odd)
 
 
 def test_fused_and_recompute_modes_agree_bitwise(L):
