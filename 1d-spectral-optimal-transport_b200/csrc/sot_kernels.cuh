@@ -98,6 +98,10 @@ struct Layout {
     static constexpr uint32_t POS_OFF = 2 * ROW;  // cdf address -> position address (two rows; none when UNI)
     static constexpr uint32_t PROWS = UNI ? 0 : 2;
     static constexpr uint32_t G_OFF = (2 + PROWS) * ROW;  // cdf address -> dL/dCDF address (two rows; also output staging)
+    // (A separate landing zone for the raw rows, so that the next frame is fetched while this one is
+    // still being walked, was measured: the mbarrier wait disappears from the stall samples, the run
+    // time does not change -- the kernel is bound by issue slots and shared-memory wavefronts.)
+    static constexpr uint32_t LAND = A;
     static constexpr uint32_t ROWS = 2 + PROWS + ((OUT == OUT_GRAD) ? 2 : 0);
     static constexpr uint32_t SCRATCH = ROWS * ROW;               // 8 doubles per warp
     static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per chunk + end marker
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     constexpr int SEARCH_TOP = 1 << (ilog2_ceil(TPF * E + 1) - 1);
     constexpr uint32_t NO_FIX = 0xffffffffu;
     constexpr uint32_t POS4 = LY::POS_OFF + 4;
-    constexpr uint32_t LAND = LY::A;  // landing zone rows (u, then v at + ROW)
+    constexpr uint32_t LAND = LY::LAND;  // landing zone rows (u, then v at + ROW)
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int n = args.n, m = args.m, K = n + m;
@@ -387,11 +391,6 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             const float* gpv = args.pos_v + frame * args.pos_v_stride;
             for (int idx = tid; idx <= n; idx += TPF) fsm[2 * RS + idx] = gpu[min(idx, n - 1)];
             for (int idx = tid; idx <= m; idx += TPF) fsm[3 * RS + idx] = gpv[min(idx, m - 1)];
-        }
-        if constexpr (WITH_GRAD) {
-            // the previous frame's output store must have finished READING its staging rows (the dL/dCDF
-            // rows) before this frame's walk writes them again
-            if (tid == 0) bulk_wait_read_all();
         }
 
         float acc[NCH] = {};  // my part of the frame's loss
@@ -584,6 +583,11 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             // slot: G = (m*d)_group - (m*d)_next group.  It is stored one step later,
             // when the next slot is known.  (It cannot overwrite the consumed CDF entry or its position:
             // a slower thread may still load that entry as the head that ends its own range.)
+            // the previous frame's output store must have finished READING its staging rows (the dL/dCDF
+            // rows) before they are written again (walk, or stage 4 of a poisoned frame); every such write
+            // is behind a barrier that thread 0 reaches after this wait.  By now the store has had two
+            // stages to drain.
+            if (tid == 0) bulk_wait_read_all();
             if (finite) {
                 float md_prev[NCH];
                 bool inherited[NCH];  // the open group started before my chunk: its m*d is not known yet
@@ -607,7 +611,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     consumed[ch] = 0;
                     fix[ch] = NO_FIX;
                 }
-                cta_sync<TPF>();  // mailbox complete
+                cta_sync<TPF>();  // mailbox complete (and thread 0 has seen the previous output store drain)
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch)
                     if (cnt[ch] > 0) {
