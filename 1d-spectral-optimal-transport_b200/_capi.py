@@ -42,6 +42,8 @@ _V = ctypes.c_void_p
 SIGNATURES = {
     "sot_forward_device": (ctypes.c_int, [_P, _V, _V]),
     "sot_forward_backward_device": (ctypes.c_int, [_P, _V, _V, _V, _V, _V]),
+    "sot_forward_sum_device": (ctypes.c_int, [_P, _V, _V, _V]),
+    "sot_forward_backward_scaled_device": (ctypes.c_int, [_P, _V, _V, _V, _V, _V, _V]),
     "sot_scale_rows_device": (ctypes.c_int, [_V, _V, _V, ctypes.c_int64, ctypes.c_int32, _V]),
     "sot_quantiles_device": (ctypes.c_int, [_P, _V, _V, _V, _V, _V, _V, _V, _V]),
     "sot_quantile_lookup_device": (ctypes.c_int, [_V, _V, _V, _V, ctypes.c_int64, ctypes.c_int32,
@@ -164,6 +166,32 @@ def forward_backward(u, v, pos_u, pos_v, p, flags, upstream=None, want_loss=True
         _check(lib.sot_forward_backward_device(ctypes.byref(prob), _ptr(upstream), _ptr(loss), _ptr(gu), _ptr(gv),
                                                _stream(u.device)))
     return loss, gu, gv
+
+
+def forward_sum(u, v, pos_u, pos_v, p, flags, want_rows=False):
+    """Sum over frames of the per-frame loss as a (1,) float64 device tensor (+ the rows if asked)."""
+    lib = load()
+    prob = make_problem(u, v, pos_u, pos_v, p, flags)
+    total = torch.zeros(1, dtype=torch.float64, device=u.device)
+    rows = torch.empty(u.shape[0], dtype=torch.float32, device=u.device) if want_rows else None
+    with torch.cuda.device(u.device):
+        _check(lib.sot_forward_sum_device(ctypes.byref(prob), _ptr(rows), _ptr(total), _stream(u.device)))
+    return total, rows
+
+
+def forward_backward_scaled(u, v, pos_u, pos_v, p, flags, scale, want_gu=True, want_gv=True):
+    """Gradients of scale * sum_n loss_n; `scale` is a (1,) float32 DEVICE tensor (no host sync)."""
+    lib = load()
+    prob = make_problem(u, v, pos_u, pos_v, p, flags)
+    _dev_tensor(scale, "scale")
+    if scale.numel() != 1:
+        raise ValueError("sot_b200: the upstream scale must hold one element")
+    gu = torch.empty_like(u) if want_gu else None
+    gv = torch.empty_like(v) if want_gv else None
+    with torch.cuda.device(u.device):
+        _check(lib.sot_forward_backward_scaled_device(ctypes.byref(prob), None, _ptr(scale), None, _ptr(gu), _ptr(gv),
+                                                      _stream(u.device)))
+    return gu, gv
 
 
 def scale_rows(unit, scale) -> torch.Tensor:

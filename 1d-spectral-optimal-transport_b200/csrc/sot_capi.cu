@@ -222,6 +222,27 @@ int sot_forward_backward_device(const sot_problem* prob, const float* upstream, 
     return launch(prob, r, stream);
 }
 
+int sot_forward_sum_device(const sot_problem* prob, float* loss, double* loss_sum, void* stream) {
+    if (int rc = validate(prob)) return rc;
+    if (loss_sum == nullptr) return fail(SOT_EINVAL, "loss_sum is NULL");
+    sot::LaunchRequest r{base_args(prob), sot::OUT_LOSS, sot::MODE_SPECTRA};
+    r.args.loss = loss;
+    r.args.loss_sum = loss_sum;
+    return launch(prob, r, stream);
+}
+
+int sot_forward_backward_scaled_device(const sot_problem* prob, const float* upstream, const float* upstream_scale,
+                                       float* loss, float* grad_u, float* grad_v, void* stream) {
+    if (int rc = validate(prob)) return rc;
+    sot::LaunchRequest r{base_args(prob), sot::OUT_GRAD, sot::MODE_SPECTRA};
+    r.args.upstream = upstream;
+    r.args.upstream_scale = upstream_scale;
+    r.args.loss = loss;
+    r.args.grad_u = grad_u;
+    r.args.grad_v = grad_v;
+    return launch(prob, r, stream);
+}
+
 int sot_scale_rows_device(const float* unit, const float* scale, float* out, int64_t rows, int32_t width,
                           void* stream) {
     if (rows < 0 || width < 1) return fail(SOT_EINVAL, "bad sizes: rows=%lld width=%d", (long long)rows, width);

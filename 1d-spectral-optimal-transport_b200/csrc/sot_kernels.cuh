@@ -68,8 +68,10 @@ struct FrameArgs {
     const float* pos_v;
     long long pos_u_stride;  // 0: one shared support row; else elements between per-frame rows
     long long pos_v_stride;
-    const float* upstream;  // [n_frames] dL_total/dloss_n, or nullptr (= 1)
-    float* loss;            // [n_frames] or nullptr
+    const float* upstream;        // [n_frames] dL_total/dloss_n, or nullptr (= 1)
+    const float* upstream_scale;  // device scalar multiplying every upstream value, or nullptr (= 1)
+    float* loss;                  // [n_frames] or nullptr
+    double* loss_sum;             // device scalar: += sum of the per-frame losses of this launch, or nullptr
     float* grad_u;          // [n_frames, n] or nullptr
     float* grad_v;          // [n_frames, m] or nullptr
     // OUT_PLAN outputs, each nullable: [n_frames, n+m] merged grid, un-clamped lower-bound indices
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
 
     long long frame = blockIdx.x;
     uint32_t parity = 0;
+    double cta_loss = 0.0;  // (thread 0) sum of the losses of the frames this CTA processed
     // state of the frame in flight: phases of its two rows and whether it comes by bulk copy
     uint32_t lead_in_u = 0, lead_in_v = 0;
     bool bulk_in = false;
@@ -760,7 +763,11 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             } else {
                 __syncwarp();
             }
-            if (tid == 0 && args.loss != nullptr) args.loss[frame] = finite ? static_cast<float>(part) : f_nan();
+            if (tid == 0) {
+                const float frame_loss = finite ? static_cast<float>(part) : f_nan();
+                if (args.loss != nullptr) args.loss[frame] = frame_loss;
+                cta_loss += static_cast<double>(frame_loss);
+            }
         }
 
         if constexpr (!WITH_GRAD) {
@@ -828,7 +835,8 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 const double corr_v = (!cut_scale && v_live) ? dot_v : 0.0;
                 // gw = offset + local suffix; (offset - corr) is formed in fp64 before rounding
                 const float bu = static_cast<float>(off_u - corr_u), bv = static_cast<float>(off_v - corr_v);
-                const float up = args.upstream != nullptr ? args.upstream[frame] : 1.0f;
+                const float up = (args.upstream != nullptr ? args.upstream[frame] : 1.0f) *
+                                 (args.upstream_scale != nullptr ? *args.upstream_scale : 1.0f);
                 const float ku = finite ? static_cast<float>(inv_u) * up * (square ? 2.0f : 1.0f) : f_nan();
                 const float kv = finite ? static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f) : f_nan();
 #pragma unroll
@@ -886,6 +894,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             }
         }
     }
+    if (tid == 0 && args.loss_sum != nullptr) atomicAdd(args.loss_sum, cta_loss);  // one atomic per CTA
     if constexpr (WITH_GRAD) {
         if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store
     }

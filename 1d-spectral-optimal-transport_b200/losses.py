@@ -17,9 +17,10 @@ import torch
 
 from . import _capi
 
-__all__ = ["Wasserstein1D", "wasserstein_1d", "quantile_function", "sot_frames"]
+__all__ = ["Wasserstein1D", "wasserstein_1d", "quantile_function", "sot_frames", "sot_mean"]
 
 BACKWARD_MODES = ("recompute", "fused")
+_LOCAL_ONLY = object()  # sentinel "process group": never reduce across ranks
 
 
 # --------------------------------------------------------------------------------------
@@ -173,12 +174,9 @@ def _uniform_grid(pu: torch.Tensor, pv: torch.Tensor, owner_u: torch.Tensor, own
     return uniform
 
 
-def sot_frames(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=False, require_sort=True,
-               raw_weights=False, backward_mode="recompute") -> torch.Tensor:
-    """Per-frame W_p^p, shape (N,), differentiable w.r.t. x and y."""
+def _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights):
+    """Reference prologue that stays on the host: flatten, canonicalise supports, hoisted sort."""
     assert p >= 1, f"The OT loss is only valid for p>=1, {p} was given"  # losses.py:271
-    if backward_mode not in BACKWARD_MODES:
-        raise ValueError(f"backward_mode must be one of {BACKWARD_MODES}")
     u, v = _rows(x, "x"), _rows(y, "y")
     if u.shape[0] != v.shape[0]:
         raise ValueError(f"sot_b200: x has {u.shape[0]} frames, y has {v.shape[0]}")
@@ -191,7 +189,65 @@ def sot_frames(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=Fal
     flags = ((_capi.SOT_SQUARE if square else 0) | (_capi.SOT_CUT_SCALE if cut_scale else 0) |
              (_capi.SOT_LIMIT if limit else 0) | (_capi.SOT_RAW_WEIGHTS if raw_weights else 0) |
              (_capi.SOT_UNIFORM_GRID if _uniform_grid(pu, pv, x_pos, y_pos) else 0))
+    return u, v, pu, pv, flags
+
+
+def sot_frames(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=False, require_sort=True,
+               raw_weights=False, backward_mode="recompute") -> torch.Tensor:
+    """Per-frame W_p^p, shape (N,), differentiable w.r.t. x and y."""
+    if backward_mode not in BACKWARD_MODES:
+        raise ValueError(f"backward_mode must be one of {BACKWARD_MODES}")
+    u, v, pu, pv, flags = _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights)
     return _SotFrames.apply(u, v, pu, pv, float(p), flags, backward_mode)
+
+
+class _SotMean(torch.autograd.Function):
+    """rows (N, n), (N, m) -> mean over the frames of ALL ranks of W_p^p, a 0-dim tensor.
+
+    The mean the reference takes at the end (losses.py:211) folded into the two launches: the forward
+    kernel accumulates the sum of the per-frame losses on the device (one fp64 atomic per CTA), the
+    backward kernel reads dL/dmean / N from a device scalar.  No reduction kernel, no per-frame
+    upstream vector, no host synchronisation.  With a process group the only collective is one
+    all-reduce of (sum, count)."""
+
+    @staticmethod
+    def forward(ctx, u, v, pos_u, pos_v, p, flags, group):
+        import torch.distributed as dist
+        total, _ = _capi.forward_sum(u, v, pos_u, pos_v, p, flags)
+        count = float(u.shape[0])
+        ctx.p, ctx.flags = p, flags
+        ctx.need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        if group is not _LOCAL_ONLY and dist.is_available() and dist.is_initialized() and \
+                dist.get_world_size(group) > 1:
+            stats = torch.cat((total, torch.full_like(total, count)))
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+            ctx.count = None
+            ctx.save_for_backward(u, v, pos_u, pos_v, stats[1:2])
+            return (stats[0] / stats[1]).to(torch.float32)
+        ctx.count = count
+        ctx.save_for_backward(u, v, pos_u, pos_v)
+        return (total[0] / count).to(torch.float32)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        if ctx.count is None:
+            u, v, pos_u, pos_v, count = ctx.saved_tensors
+            scale = (grad_out.to(torch.float64) / count).to(torch.float32).reshape(1)
+        else:
+            u, v, pos_u, pos_v = ctx.saved_tensors
+            scale = (grad_out / ctx.count).to(torch.float32).reshape(1)
+        gu, gv = _capi.forward_backward_scaled(u, v, pos_u, pos_v, ctx.p, ctx.flags, scale.contiguous(),
+                                               ctx.need[0], ctx.need[1])
+        return gu, gv, None, None, None, None, None
+
+
+def sot_mean(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=False, require_sort=True,
+             raw_weights=False, group=None) -> torch.Tensor:
+    """mean_n W_p^p(frame n) over this rank's frames -- and over all ranks' when `group` (or the default
+    process group) spans more than one -- differentiable w.r.t. x and y.  Two kernel launches a step."""
+    u, v, pu, pv, flags = _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights)
+    return _SotMean.apply(u, v, pu, pv, float(p), flags, group)
 
 
 # --------------------------------------------------------------------------------------
@@ -216,6 +272,11 @@ class Wasserstein1D(torch.nn.Module):
         else:
             self.register_buffer("fixed_x", None)
 
+    def _mean_group(self):
+        """Process group whose ranks share the final mean; the single-process reference has none.
+        `sharding.ShardedWasserstein1D` overrides this."""
+        return _LOCAL_ONLY
+
     def forward(self, x, y, x_pos=None, y_pos=None, **kwargs):
         if (x_pos is None or y_pos is None) and self.fixed_x is None:
             raise ValueError("If fixed_x is not provided, x_pos and y_pos must be provided")
@@ -236,9 +297,13 @@ class Wasserstein1D(torch.nn.Module):
             out = _quantiles(x, y, x_pos_, y_pos_, bool(self.square_dist), cut_scale, need_sort)
             return [t.reshape(original_shape + (-1,)) for t in out]  # losses.py:198-201
 
+        mode = getattr(self, "backward_mode", "recompute")
+        if not self.hinge and kwargs.get("dims", None) is None and mode == "recompute" and x.numel() > 0:
+            # plain mean over all frames (every paper config): folded into the two kernel launches
+            return sot_mean(x, y, x_pos_, y_pos_, p=self.p, square=bool(self.square_dist), cut_scale=cut_scale,
+                            limit=limit, require_sort=need_sort, group=self._mean_group())
         loss = sot_frames(x, y, x_pos_, y_pos_, p=self.p, square=bool(self.square_dist), cut_scale=cut_scale,
-                          limit=limit, require_sort=need_sort,
-                          backward_mode=getattr(self, "backward_mode", "recompute"))
+                          limit=limit, require_sort=need_sort, backward_mode=mode)
         if self.hinge:  # losses.py:203-205: the ctor flag gates, the call kwarg is the threshold
             loss = torch.nn.functional.relu(loss - kwargs.get("hinge", 0.0))
         loss = loss.reshape(original_shape)

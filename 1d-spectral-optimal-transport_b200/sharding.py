@@ -55,15 +55,21 @@ def global_mean(rows: torch.Tensor, group=None) -> torch.Tensor:
 
 class ShardedWasserstein1D(losses.Wasserstein1D):
     """`Wasserstein1D` whose inputs are this rank's slice of the batch and whose value is the mean
-    over the whole (all-rank) batch.  Same constructor; `dims` other than None is not sharded."""
+    over the whole (all-rank) batch.  Same constructor plus `process_group` (None = the default
+    group).  `dims` other than None and `return_quantiles` stay local."""
 
     def __init__(self, *args, process_group=None, **kwargs):
         super().__init__(*args, **kwargs)
         self.process_group = process_group
 
+    def _mean_group(self):
+        return self.process_group
+
     def forward(self, x, y, x_pos=None, y_pos=None, **kwargs):
         if kwargs.get("dims", None) is not None or kwargs.get("return_quantiles", False):
             return super().forward(x, y, x_pos=x_pos, y_pos=y_pos, **kwargs)
+        if not self.hinge and getattr(self, "backward_mode", "recompute") == "recompute" and x.numel() > 0:
+            return super().forward(x, y, x_pos=x_pos, y_pos=y_pos, **kwargs)  # fused global mean
         if (x_pos is None or y_pos is None) and self.fixed_x is None:
             raise ValueError("If fixed_x is not provided, x_pos and y_pos must be provided")
         x_pos_ = self.fixed_x if x_pos is None else x_pos

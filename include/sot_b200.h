@@ -75,6 +75,16 @@ int sot_forward_device(const sot_problem* prob, float* loss, void* stream);
 int sot_forward_backward_device(const sot_problem* prob, const float* upstream, float* loss,
                                 float* grad_u, float* grad_v, void* stream);
 
+/* The reference ends with `torch.mean` over all frames (losses.py:211).  These two fold that mean
+ * into the launches: the forward also accumulates *loss_sum += sum_n loss[n] (fp64, one atomic per
+ * CTA; the caller zeroes it; `loss` may be NULL), and the backward takes the upstream gradient as
+ * upstream[n] * (*upstream_scale) with both factors optional -- for a mean, upstream = NULL and
+ * *upstream_scale = dL/dmean / N, a DEVICE scalar, so no host synchronisation is needed. */
+int sot_forward_sum_device(const sot_problem* prob, float* loss, double* loss_sum, void* stream);
+int sot_forward_backward_scaled_device(const sot_problem* prob, const float* upstream,
+                                       const float* upstream_scale, float* loss, float* grad_u,
+                                       float* grad_v, void* stream);
+
 /* out[r, :] = unit[r, :] * scale[r]  -- backward of the "fused" autograd mode, where the forward
  * launch already produced the unit gradients. */
 int sot_scale_rows_device(const float* unit, const float* scale, float* out, int64_t rows,

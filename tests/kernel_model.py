@@ -1,11 +1,13 @@
-"""Executable model (numpy, scalar loops) of what ONE frame group of the CUDA kernel does.
+"""Executable model (numpy, scalar loops) of the ALGORITHM the CUDA kernel runs for one frame.
 
-It mirrors `csrc/sot_kernels.cuh` step for step -- merge-path partition per thread, the per-thread
-sequential walk with tie-group tracking, the one-slot peek across the thread boundary, the
-look-back carry for a tie group inherited from earlier threads, the scatter of dL/dCDF to the
-source entries, the two suffix scans and the normalisation chain rule -- so the *algorithm* can
-be checked against the oracle on the CPU (tests/test_kernel_model.py) before and independently of
-any GPU run.  Test infrastructure only.
+It follows `csrc/sot_kernels.cuh` stage by stage -- merge-path partition per chunk, the sequential
+walk with tie-group tracking, the one-slot peek across the chunk boundary, the look-back carry
+for a tie group inherited from earlier chunks, the scatter of dL/dCDF to the source entries, the
+two suffix scans and the normalisation chain rule -- so the algorithm can be checked against the
+oracle on the CPU (tests/test_kernel_model.py) before and independently of any GPU run.
+Differences in arithmetic detail that the GPU tests (not this model) pin down: the kernel forms
+the CDF as fl32(prefix64 / mass) instead of cumsum64(fl32(a / mass)), obtains the mass term by
+Abel summation sum(dL/dc * c), and cuts the slots into odd-length chunks.  Test infrastructure only.
 """
 import numpy as np
 

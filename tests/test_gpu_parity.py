@@ -278,6 +278,33 @@ def test_module_detects_uniform_grids(L):
     assert not L._uniform_grid(odd, odd, odd, odd)
 
 
+def test_fused_mean_path_matches_the_per_frame_path(capi, L):
+    """Wasserstein1D(...)(x, y) takes the two-launch path with the mean folded into the kernels;
+    it must agree with mean(per-frame rows) and its gradients with the rows path."""
+    g = G.load("sot2048_cut")
+    ctor = g["meta"]["ctor"]
+    px, py = g["pos_x"].to(DEV), g["pos_y"].to(DEV)
+    x1 = g["x"].to(DEV).requires_grad_(True)
+    y1 = g["y"].to(DEV).requires_grad_(True)
+    before = capi.launch_count()
+    v1 = L.Wasserstein1D(**ctor)(x1, y1, x_pos=px, y_pos=py)
+    (0.5 * v1).backward()
+    assert capi.launch_count() - before == 2, "one forward and one backward launch"
+    assert v1.ndim == 0 and v1.dtype == torch.float32
+    x2 = g["x"].to(DEV).requires_grad_(True)
+    y2 = g["y"].to(DEV).requires_grad_(True)
+    rows = L.sot_frames(x2, y2, px, py, p=2, square=True, cut_scale=True, limit=True)
+    v2 = rows.mean()
+    (0.5 * v2).backward()
+    assert abs(v1.item() - v2.item()) <= 1e-6 * abs(v2.item())
+    assert torch.allclose(x1.grad, x2.grad, rtol=1e-6, atol=0) and torch.allclose(y1.grad, y2.grad, rtol=1e-6, atol=0)
+    # inference_mode / no grad: one launch
+    before = capi.launch_count()
+    with torch.inference_mode():
+        v3 = L.Wasserstein1D(**ctor)(g["x"].to(DEV), g["y"].to(DEV), x_pos=px, y_pos=py)
+    assert capi.launch_count() - before == 1 and abs(v3.item() - v2.item()) <= 1e-6 * abs(v2.item())
+
+
 def test_fused_and_recompute_modes_agree_bitwise(L):
     g = G.load("sot2048_cut")
     outs = []
