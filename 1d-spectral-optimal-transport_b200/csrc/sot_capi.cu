@@ -222,17 +222,29 @@ int sot_forward_backward_device(const sot_problem* prob, const float* upstream, 
     return launch(prob, r, stream);
 }
 
-int sot_forward_sum_device(const sot_problem* prob, float* loss, double* loss_sum, void* stream) {
+int sot_coranks_per_frame(int32_t n_u, int32_t n_v) {
+    const Config* c = pick_config(n_u, n_v);
+    return c == nullptr ? 0 : c->tpf * c->nch;
+}
+
+int sot_forward_sum_device(const sot_problem* prob, float* loss, double* loss_sum, uint16_t* coranks_out,
+                           int32_t coranks_per_frame, void* stream) {
     if (int rc = validate(prob)) return rc;
-    if (loss_sum == nullptr) return fail(SOT_EINVAL, "loss_sum is NULL");
     sot::LaunchRequest r{base_args(prob), sot::OUT_LOSS, sot::MODE_SPECTRA};
     r.args.loss = loss;
     r.args.loss_sum = loss_sum;
+    if (coranks_out != nullptr) {
+        if (coranks_per_frame != sot_coranks_per_frame(prob->n_u, prob->n_v))
+            return fail(SOT_EINVAL, "coranks_per_frame = %d, this configuration needs %d", coranks_per_frame,
+                        sot_coranks_per_frame(prob->n_u, prob->n_v));
+        r.args.coranks_out = coranks_out;
+    }
     return launch(prob, r, stream);
 }
 
 int sot_forward_backward_scaled_device(const sot_problem* prob, const float* upstream, const float* upstream_scale,
-                                       float* loss, float* grad_u, float* grad_v, void* stream) {
+                                       const uint16_t* coranks_in, int32_t coranks_per_frame, float* loss,
+                                       float* grad_u, float* grad_v, void* stream) {
     if (int rc = validate(prob)) return rc;
     sot::LaunchRequest r{base_args(prob), sot::OUT_GRAD, sot::MODE_SPECTRA};
     r.args.upstream = upstream;
@@ -240,6 +252,9 @@ int sot_forward_backward_scaled_device(const sot_problem* prob, const float* ups
     r.args.loss = loss;
     r.args.grad_u = grad_u;
     r.args.grad_v = grad_v;
+    // co-ranks saved by a launch of another configuration are useless: search again instead
+    if (coranks_in != nullptr && coranks_per_frame == sot_coranks_per_frame(prob->n_u, prob->n_v))
+        r.args.coranks_in = coranks_in;
     return launch(prob, r, stream);
 }
 

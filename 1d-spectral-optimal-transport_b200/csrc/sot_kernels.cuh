@@ -72,6 +72,11 @@ struct FrameArgs {
     const float* upstream_scale;  // device scalar multiplying every upstream value, or nullptr (= 1)
     float* loss;                  // [n_frames] or nullptr
     double* loss_sum;             // device scalar: += sum of the per-frame losses of this launch, or nullptr
+    // "saved merge indices": the merge-path co-rank (number of u entries before the chunk) of every
+    // chunk of every frame, [n_frames, NCH * TPF] uint16.  The forward launch can save them, the backward
+    // launch of the same configuration can reuse them instead of searching again (both nullable).
+    unsigned short* coranks_out;
+    const unsigned short* coranks_in;
     float* grad_u;          // [n_frames, n] or nullptr
     float* grad_v;          // [n_frames, m] or nullptr
     // OUT_PLAN outputs, each nullable: [n_frames, n+m] merged grid, un-clamped lower-bound indices
@@ -401,6 +406,10 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         double inv_u = 1.0, inv_v = 1.0;
         bool u_live = false, v_live = false;  // mass above the safe_divide floor -> carries gradient
         float xu[E], xv[E];                   // raw bins (the gradient kernel needs them again at the end)
+        int saved_corank[NCH];                // (loaded early: the global-memory latency hides behind stage 2)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            saved_corank[ch] = args.coranks_in != nullptr ? min(static_cast<int>(args.coranks_in[frame * NCHUNK + NCH * tid + ch]), n) : 0;
         (void)inv_v;
         (void)u_live;
         (void)v_live;
@@ -504,7 +513,11 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             a[ch] = pa[ch] = b[ch] = pb[ch] = qprev[ch] = 0.0f;
             i0[ch] = 0;
         }
-        if (finite) {
+        if (finite && args.coranks_in != nullptr) {
+            // ---- stage 3a': the forward launch already found the co-ranks (same CDFs, bit for bit) ------
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) i0[ch] = saved_corank[ch];
+        } else if (finite) {
             // ---- stage 3a: merge-path partition (fixed-trip, branch-free bit descent) ---------------
             // i0 = number of u entries among the first k0 merged slots (u first on equal values):
             // the largest i in [lo, hi] with A[i-1] <= B[k0-i].  The NCH searches are interleaved.
@@ -528,8 +541,16 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 }
             }
 #pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) i0[ch] = static_cast<int>((cur[ch] - A0) >> 2);
+        }
+        if (finite) {
+            if (args.coranks_out != nullptr) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch)
+                    args.coranks_out[frame * NCHUNK + NCH * tid + ch] = static_cast<unsigned short>(i0[ch]);
+            }
+#pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                i0[ch] = static_cast<int>((cur[ch] - A0) >> 2);
                 adrA[ch] = A0 + 4u * i0[ch];
                 adrB[ch] = B0 + 4u * (k0[ch] - i0[ch]);
                 a[ch] = lds32(adrA[ch]);

@@ -213,7 +213,9 @@ class _SotMean(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, v, pos_u, pos_v, p, flags, group):
         import torch.distributed as dist
-        total, _ = _capi.forward_sum(u, v, pos_u, pos_v, p, flags)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        total, _, coranks = _capi.forward_sum(u, v, pos_u, pos_v, p, flags, save_coranks=need_grad)
+        ctx.coranks = coranks  # merge indices saved for the backward launch (not a differentiable input)
         count = float(u.shape[0])
         ctx.p, ctx.flags = p, flags
         ctx.need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
@@ -238,7 +240,7 @@ class _SotMean(torch.autograd.Function):
             u, v, pos_u, pos_v = ctx.saved_tensors
             scale = (grad_out / ctx.count).to(torch.float32).reshape(1)
         gu, gv = _capi.forward_backward_scaled(u, v, pos_u, pos_v, ctx.p, ctx.flags, scale.contiguous(),
-                                               ctx.need[0], ctx.need[1])
+                                               ctx.coranks, ctx.need[0], ctx.need[1])
         return gu, gv, None, None, None, None, None
 
 

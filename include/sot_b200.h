@@ -80,10 +80,17 @@ int sot_forward_backward_device(const sot_problem* prob, const float* upstream, 
  * CTA; the caller zeroes it; `loss` may be NULL), and the backward takes the upstream gradient as
  * upstream[n] * (*upstream_scale) with both factors optional -- for a mean, upstream = NULL and
  * *upstream_scale = dL/dmean / N, a DEVICE scalar, so no host synchronisation is needed. */
-int sot_forward_sum_device(const sot_problem* prob, float* loss, double* loss_sum, void* stream);
+int sot_forward_sum_device(const sot_problem* prob, float* loss, double* loss_sum, uint16_t* coranks_out,
+                           int32_t coranks_per_frame, void* stream);
 int sot_forward_backward_scaled_device(const sot_problem* prob, const float* upstream,
-                                       const float* upstream_scale, float* loss, float* grad_u,
-                                       float* grad_v, void* stream);
+                                       const float* upstream_scale, const uint16_t* coranks_in,
+                                       int32_t coranks_per_frame, float* loss, float* grad_u, float* grad_v,
+                                       void* stream);
+/* "Saved merge indices": the forward launch can write the merge-path co-rank of every chunk of every
+ * frame into coranks_out[n_frames, sot_coranks_per_frame(n_u, n_v)] (nullable) and the backward launch
+ * reuse them (coranks_in, nullable) instead of repeating the search -- the CDFs of the two launches are
+ * bit-identical.  Co-ranks from another kernel configuration (other count) are ignored. */
+int sot_coranks_per_frame(int32_t n_u, int32_t n_v);
 
 /* out[r, :] = unit[r, :] * scale[r]  -- backward of the "fused" autograd mode, where the forward
  * launch already produced the unit gradients. */

@@ -305,6 +305,30 @@ def test_fused_mean_path_matches_the_per_frame_path(capi, L):
     assert capi.launch_count() - before == 1 and abs(v3.item() - v2.item()) <= 1e-6 * abs(v2.item())
 
 
+def test_saved_merge_indices_give_bit_identical_gradients(capi):
+    g = G.load("sot2048_cut")
+    F = 1025
+    x, y = g["x"].reshape(-1, F).to(DEV), g["y"].reshape(-1, F).to(DEV)
+    pos = g["pos_x"].to(DEV)
+    scale = torch.full((1,), 0.125, device=DEV)
+    for flags in (capi.SOT_SQUARE, capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT | capi.SOT_UNIFORM_GRID):
+        total, rows, coranks = capi.forward_sum(x, y, pos, pos, 2.0, flags, want_rows=True, save_coranks=True)
+        assert coranks.shape == (x.shape[0], capi.load().sot_coranks_per_frame(F, F)) and coranks.dtype == torch.int16
+        assert (coranks >= 0).all() and (coranks <= F).all() and (coranks[:, 0] == 0).all()
+        assert (coranks[:, 1:] >= coranks[:, :-1]).all(), "co-ranks are non-decreasing along the merge path"
+        assert total.item() == pytest.approx(rows.double().sum().item(), rel=1e-12)
+        a = capi.forward_backward_scaled(x, y, pos, pos, 2.0, flags, scale, coranks=coranks)
+        b = capi.forward_backward_scaled(x, y, pos, pos, 2.0, flags, scale, coranks=None)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        # co-ranks of another configuration are ignored, not misused
+        capi.set_tuning(128, 9, 1)
+        try:
+            c = capi.forward_backward_scaled(x, y, pos, pos, 2.0, flags, scale, coranks=coranks)
+        finally:
+            capi.set_tuning(0, 0, 0)
+        assert (c[0] - b[0]).norm() <= 1e-4 * b[0].norm()
+
+
 def test_fused_and_recompute_modes_agree_bitwise(L):
     g = G.load("sot2048_cut")
     outs = []
