@@ -61,6 +61,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
+    wanted = {os.path.basename(src)[:-3] for src in _sources()}
+    for old in glob.glob(os.path.join(OBJ_DIR, "*")):  # objects of configurations that no longer exist
+        if os.path.basename(old).split(".")[0] not in wanted:
+            os.remove(old)
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(_compile, _sources()))
     cmd = [_nvcc(), "-shared", "-o", LIB_PATH + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
