@@ -13,7 +13,7 @@ import torch
 
 from . import build as _build
 
-SOT_SQUARE, SOT_CUT_SCALE, SOT_LIMIT, SOT_RAW_WEIGHTS, SOT_UNIFORM_GRID = 1, 2, 4, 8, 16
+SOT_SQUARE, SOT_CUT_SCALE, SOT_LIMIT, SOT_RAW_WEIGHTS, SOT_UNIFORM_GRID, SOT_COMPLEX_INPUT = 1, 2, 4, 8, 16, 32
 ABI_VERSION = 1
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers
@@ -104,12 +104,12 @@ def _check(rc: int):
     raise SotError(f"sot_b200 CUDA error {rc}: {msg}")
 
 
-def _dev_tensor(t: torch.Tensor, name: str) -> torch.Tensor:
+def _dev_tensor(t: torch.Tensor, name: str, complex_ok: bool = False) -> torch.Tensor:
     if not t.is_cuda:
         raise SotError(f"sot_b200: `{name}` lives on {t.device}; the SOT kernels are CUDA only "
                        "(no CPU fallback exists by design)")
-    if t.dtype != torch.float32:
-        raise TypeError(f"sot_b200: `{name}` must be float32, got {t.dtype}")
+    if t.dtype != torch.float32 and not (complex_ok and t.dtype == torch.complex64):
+        raise TypeError(f"sot_b200: `{name}` must be float32{' or complex64' if complex_ok else ''}, got {t.dtype}")
     return t
 
 
@@ -122,8 +122,15 @@ def _stream(device) -> ctypes.c_void_p:
 
 
 def make_problem(u, v, pos_u, pos_v, p: float, flags: int) -> SotProblem:
-    """u: (N, n), v: (N, m) contiguous CUDA float32; pos_*: (n,) shared or (N, n) per frame."""
-    _dev_tensor(u, "x"), _dev_tensor(v, "y"), _dev_tensor(pos_u, "x_pos"), _dev_tensor(pos_v, "y_pos")
+    """u: (N, n), v: (N, m) contiguous CUDA float32; pos_*: (n,) shared or (N, n) per frame.
+
+    u and v may both be complex64 STFT rows instead: the magnitude is then formed inside the kernel
+    (SOT_COMPLEX_INPUT is added to the flags) and the gradients come back as complex64 rows."""
+    _dev_tensor(u, "x", True), _dev_tensor(v, "y", True), _dev_tensor(pos_u, "x_pos"), _dev_tensor(pos_v, "y_pos")
+    if u.dtype != v.dtype:
+        raise TypeError(f"sot_b200: `x` and `y` must have the same dtype, got {u.dtype} and {v.dtype}")
+    if u.is_complex():
+        flags = int(flags) | SOT_COMPLEX_INPUT
     if u.ndim != 2 or v.ndim != 2 or u.shape[0] != v.shape[0]:
         raise ValueError(f"sot_b200: expected (N, n) and (N, m) rows, got {tuple(u.shape)} and {tuple(v.shape)}")
     if not (u.is_contiguous() and v.is_contiguous() and pos_u.is_contiguous() and pos_v.is_contiguous()):

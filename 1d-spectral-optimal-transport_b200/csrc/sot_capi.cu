@@ -135,7 +135,7 @@ int validate(const sot_problem* p) {
     if (p->pos_u_stride < 0 || p->pos_v_stride < 0) return fail(SOT_EINVAL, "negative position stride");
     if (!(p->p >= 1.0f))  // also rejects NaN; losses.py:271
         return fail(SOT_EDOMAIN, "The OT loss is only valid for p>=1, %g was given", (double)p->p);
-    if (p->flags & ~(SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS | SOT_UNIFORM_GRID))
+    if (p->flags & ~(SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS | SOT_UNIFORM_GRID | SOT_COMPLEX_INPUT))
         return fail(SOT_EINVAL, "unknown flag bits");
     if ((p->n_frames + 3) / 4 > 0x7fffffffLL) return fail(SOT_ETOOBIG, "too many frames for one launch");
     return SOT_OK;
@@ -159,11 +159,17 @@ sot::FrameArgs base_args(const sot_problem* p) {
 }
 
 int launch(const sot_problem* p, sot::LaunchRequest& r, void* stream) {
+    if ((p->flags & SOT_COMPLEX_INPUT) && (r.mode != sot::MODE_SPECTRA || r.out == sot::OUT_PLAN))
+        return fail(SOT_EINVAL, "SOT_COMPLEX_INPUT is only valid for the forward / forward+backward entry points");
     if (p->n_frames == 0) return SOT_OK;
     const Config* c = pick_config(p->n_u, p->n_v);
     if (c == nullptr)
         return fail(SOT_ETOOBIG, "rows of %d / %d bins exceed the largest kernel configuration (%d bins)", p->n_u,
                     p->n_v, sot_max_bins(1, 1));
+    // complex input keeps two double-width landing rows on top of the real rows: up to 10 rows of 4*rs bytes
+    if ((p->flags & SOT_COMPLEX_INPUT) && 40 * c->rs + 1024 > 227 * 1024)
+        return fail(SOT_ETOOBIG, "complex rows of %d / %d bins do not fit in shared memory (limit %d bins)", p->n_u,
+                    p->n_v, 4352);
     cudaError_t e = c->fn(r, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "sot_frames_kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);

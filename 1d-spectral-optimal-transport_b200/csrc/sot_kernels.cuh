@@ -23,6 +23,9 @@
 //               pos[0] + i*h exactly, so these two rows and the position load of every merged slot
 //               disappear -- the position difference of the two heads is tracked with exact +-h steps.
 //   next 2    : (gradient kernel) dL/dCDF of u / v
+//   next 4    : (complex input, template flag CPLX) the two interleaved complex64 STFT rows: the
+//               magnitude (squared) is formed while they are read -- no |.| tensor in HBM -- and the
+//               gradient kernel overwrites them in place with the complex gradient rows
 //   then      : scan scratch, first-slot mailbox + carry per chunk, mbarrier
 // The raw rows of a frame arrive by TMA bulk copy (`cp.async.bulk`, SASS UBLKCP).  A 4*n-byte row
 // is only 4-byte aligned (n = 1025 / 257), the bulk unit is 16 bytes: the copy therefore fetches
@@ -46,6 +49,7 @@ enum : int {
     FLAG_LIMIT = 4,      // limit_quantile_range losses.py:306-307
     FLAG_RAW = 8,        // rows are weights used as given (module-level wasserstein_1d, :223-313)
     FLAG_UNIFORM = 16,   // caller asserts: shared supports with pos[i] = pos[0] + i*h EXACTLY in fp32
+    FLAG_COMPLEX = 32,   // u, v (and the gradients) are interleaved complex64 STFT rows: |z| is fused in
 };
 
 enum : int {
@@ -98,7 +102,7 @@ SOT_DEVINL float f_inf() { return __int_as_float(0x7f800000); }
 SOT_DEVINL float f_nan() { return __int_as_float(0x7fc00000); }
 
 // ---- compile-time shared-memory layout ---------------------------------------------------------
-template <int TPF, int RS, int OUT, int NCH, bool UNI>
+template <int TPF, int RS, int OUT, int NCH, bool UNI, bool CPLX>
 struct Layout {
     static constexpr uint32_t ROW = 4u * RS;
     static constexpr uint32_t A = 0, B = ROW;     // CDF rows (also the landing zone of the raw rows)
@@ -108,8 +112,12 @@ struct Layout {
     // (A separate landing zone for the raw rows, so that the next frame is fetched while this one is
     // still being walked, was measured: the mbarrier wait disappears from the stall samples, the run
     // time does not change -- the kernel is bound by issue slots and shared-memory wavefronts.)
-    static constexpr uint32_t LAND = A;
-    static constexpr uint32_t ROWS = 2 + PROWS + ((OUT == OUT_GRAD) ? 2 : 0);
+    // Complex (STFT) input: the raw rows are twice as wide, land in their own two double rows and, in the
+    // gradient kernel, are overwritten in place by the complex gradient rows (= output staging).
+    static constexpr uint32_t REAL_ROWS = 2 + PROWS + ((OUT == OUT_GRAD) ? 2 : 0);
+    static constexpr uint32_t LAND = CPLX ? REAL_ROWS * ROW : A;
+    static constexpr uint32_t LAND_ROW = CPLX ? 2 * ROW : ROW;  // bytes between the u and the v landing row
+    static constexpr uint32_t ROWS = REAL_ROWS + (CPLX ? 4 : 0);
     static constexpr uint32_t SCRATCH = ROWS * ROW;               // 8 doubles per warp
     static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per chunk + end marker
     static constexpr uint32_t CARRY = MBOX + 8u * (NCH * TPF + 1);
@@ -286,12 +294,14 @@ SOT_DEVINL bool row_is_bulk(const float* base, long long f, int width, long long
 template <int N>
 using IC = std::integral_constant<int, N>;
 
-template <int TPF, int E, int RS, int NCH, bool UNI, int PMODE, int OUT, int MODE>
-__global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH, UNI>::TOTAL, OUT))
+template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int OUT, int MODE>
+__global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH, UNI, CPLX>::TOTAL, OUT))
     sot_frame_kernel(const FrameArgs args) {
     static_assert(NCH == 1 || NCH == 2, "one or two merge chains per thread");
     static_assert(!(UNI && OUT == OUT_PLAN), "the plan emitter always reads positions");
-    using LY = Layout<TPF, RS, OUT, NCH, UNI>;
+    static_assert(!CPLX || (MODE == MODE_SPECTRA && OUT != OUT_PLAN), "complex input: loss / gradient from spectra only");
+    using LY = Layout<TPF, RS, OUT, NCH, UNI, CPLX>;
+    constexpr int CW = CPLX ? 2 : 1;  // floats per raw bin
     constexpr int NCHUNK = NCH * TPF;
     constexpr bool WITH_GRAD = (OUT == OUT_GRAD);
     constexpr int NW = TPF / 32;
@@ -352,11 +362,12 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     (void)hstep;
     __syncthreads();
 
+    const int wu = CW * n, wv = CW * m;  // floats per raw row
     auto issue_load = [&](long long f, uint32_t lu, uint32_t lv) {  // one elected thread
-        const uint32_t bu = (lu + 4u * n + 15u) & ~15u, bv = (lv + 4u * m + 15u) & ~15u;
+        const uint32_t bu = (lu + 4u * wu + 15u) & ~15u, bv = (lv + 4u * wv + 15u) & ~15u;
         mbar_expect_tx(mbar, bu + bv);
-        bulk_g2s(smem + LAND, reinterpret_cast<const char*>(args.u + f * n) - lu, bu, mbar);
-        bulk_g2s(smem + LAND + LY::ROW, reinterpret_cast<const char*>(args.v + f * m) - lv, bv, mbar);
+        bulk_g2s(smem + LAND, reinterpret_cast<const char*>(args.u + f * wu) - lu, bu, mbar);
+        bulk_g2s(smem + LAND + LY::LAND_ROW, reinterpret_cast<const char*>(args.v + f * wv) - lv, bv, mbar);
     };
 
     long long frame = blockIdx.x;
@@ -366,33 +377,39 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     uint32_t lead_in_u = 0, lead_in_v = 0;
     bool bulk_in = false;
     if (frame < args.n_frames) {
-        lead_in_u = row_lead(args.u, frame, n);
-        lead_in_v = row_lead(args.v, frame, m);
-        bulk_in = row_is_bulk(args.u, frame, n, args.n_frames) && row_is_bulk(args.v, frame, m, args.n_frames);
+        lead_in_u = row_lead(args.u, frame, wu);
+        lead_in_v = row_lead(args.v, frame, wv);
+        bulk_in = row_is_bulk(args.u, frame, wu, args.n_frames) && row_is_bulk(args.v, frame, wv, args.n_frames);
         if (bulk_in && tid == 0) issue_load(frame, lead_in_u, lead_in_v);
     }
 
     for (; frame < args.n_frames; frame += gridDim.x) {
         // ---- stage 0: the frame's raw rows are (or get) in the landing zone ----------------------
-        uint32_t rawU = sb + LAND + 4u * e0, rawV = sb + LAND + LY::ROW + 4u * e0;  // my first raw bins
+        uint32_t rawU = sb + LAND + 4u * CW * e0, rawV = sb + LAND + LY::LAND_ROW + 4u * CW * e0;  // my first raw bins
+        uint32_t cur_lead_u = 0, cur_lead_v = 0;  // phase of this frame's raw rows inside the landing rows
         if (bulk_in) {
             mbar_wait(mbar, parity);
             parity ^= 1;
+            cur_lead_u = lead_in_u;
+            cur_lead_v = lead_in_v;
             rawU += lead_in_u;
             rawV += lead_in_v;
         } else {  // first / last row of an array whose ends are not 16-byte aligned: plain coalesced loads
-            const float* gu = args.u + frame * n;
-            const float* gv = args.v + frame * m;
-            for (int idx = tid; idx < n; idx += TPF) fsm[LAND / 4 + idx] = gu[idx];
-            for (int idx = tid; idx < m; idx += TPF) fsm[LAND / 4 + RS + idx] = gv[idx];
+            const float* gu = args.u + frame * wu;
+            const float* gv = args.v + frame * wv;
+            if constexpr (CPLX && OUT == OUT_GRAD) cta_sync<TPF>();  // thread 0 has seen the previous store drain
+            for (int idx = tid; idx < wu; idx += TPF) fsm[LAND / 4 + idx] = gu[idx];
+            for (int idx = tid; idx < wv; idx += TPF) fsm[(LAND + LY::LAND_ROW) / 4 + idx] = gv[idx];
             cta_sync<TPF>();
         }
+        (void)cur_lead_u;
+        (void)cur_lead_v;
         // the frame after this one (its load is issued further down, when the landing zone is free)
         const long long next = frame + gridDim.x;
         if (next < args.n_frames) {
-            lead_in_u = row_lead(args.u, next, n);
-            lead_in_v = row_lead(args.v, next, m);
-            bulk_in = row_is_bulk(args.u, next, n, args.n_frames) && row_is_bulk(args.v, next, m, args.n_frames);
+            lead_in_u = row_lead(args.u, next, wu);
+            lead_in_v = row_lead(args.v, next, wv);
+            bulk_in = row_is_bulk(args.u, next, wu, args.n_frames) && row_is_bulk(args.v, next, wv, args.n_frames);
         }
         if (!UNI && !pos_shared) {  // per-frame supports
             const float* gpu = args.pos_u + frame * args.pos_u_stride;
@@ -422,14 +439,23 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             {
                 double t = 0.0;
 #pragma unroll
-                for (int c = 0; c < E; ++c) xu[c] = lds32(rawU + 4 * c);  // (past the row: finite garbage inside the landing rows)
+                for (int c = 0; c < E; ++c) {  // (past the row: finite garbage inside the landing rows)
+                    if constexpr (CPLX) {  // |z|^2 = re^2 + im^2 directly (no square root), or |z|
+                        float re, im;
+                        lds64(rawU + 8 * c, re, im);
+                        const float s2 = __fmaf_rn(re, re, __fmul_rn(im, im));
+                        xu[c] = square ? s2 : sqrtf(s2);
+                    } else {
+                        xu[c] = lds32(rawU + 4 * c);
+                    }
+                }
                 if (!in_u) {
 #pragma unroll
                     for (int c = 0; c < E; ++c) xu[c] = (e0 + c < n) ? xu[c] : 0.0f;
                 }
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    t += static_cast<double>(square ? xu[c] * xu[c] : xu[c]);
+                    t += static_cast<double>((square && !CPLX) ? xu[c] * xu[c] : xu[c]);
                     P[c] = t;
                 }
                 double off = t;
@@ -451,14 +477,23 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             {
                 double t = 0.0;
 #pragma unroll
-                for (int c = 0; c < E; ++c) xv[c] = lds32(rawV + 4 * c);
+                for (int c = 0; c < E; ++c) {
+                    if constexpr (CPLX) {
+                        float re, im;
+                        lds64(rawV + 8 * c, re, im);
+                        const float s2 = __fmaf_rn(re, re, __fmul_rn(im, im));
+                        xv[c] = square ? s2 : sqrtf(s2);
+                    } else {
+                        xv[c] = lds32(rawV + 4 * c);
+                    }
+                }
                 if (!in_v) {
 #pragma unroll
                     for (int c = 0; c < E; ++c) xv[c] = (e0 + c < m) ? xv[c] : 0.0f;
                 }
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    t += static_cast<double>(square ? xv[c] * xv[c] : xv[c]);
+                    t += static_cast<double>((square && !CPLX) ? xv[c] * xv[c] : xv[c]);
                     P[c] = t;
                 }
                 double off = t;
@@ -797,11 +832,14 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         } else {
             // ---- stages 4 + 5: gradient rows, written over the dL/dCDF rows at the phase (address mod 16)
             // of their destination so that the aligned middle can leave by bulk store --------------------
-            float* const ou = args.grad_u != nullptr ? args.grad_u + frame * n : nullptr;
-            float* const ov = args.grad_v != nullptr ? args.grad_v + frame * m : nullptr;
+            float* const ou = args.grad_u != nullptr ? args.grad_u + frame * wu : nullptr;
+            float* const ov = args.grad_v != nullptr ? args.grad_v + frame * wv : nullptr;
             const uint32_t lead_u = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ou) & 15);
             const uint32_t lead_v = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ov) & 15);
             const uint32_t GA0 = A0 + LY::G_OFF, GB0 = B0 + LY::G_OFF;
+            // staging rows of the output: the dL/dCDF rows, or (complex) the landing rows, rewritten in place
+            constexpr uint32_t STAGE_U = CPLX ? LY::LAND : LY::A + LY::G_OFF;
+            constexpr uint32_t STAGE_V = CPLX ? LY::LAND + LY::LAND_ROW : LY::B + LY::G_OFF;
             if constexpr (MODE == MODE_SPECTRA) {
                 // cumsum transpose (suffix sums of dL/dCDF) and the normalisation chain rule.
                 // sum_i gw_i w_i = sum_i (dL/dc_i) c_i (Abel summation), so the mass term needs only the
@@ -850,7 +888,9 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 }
                 // every thread has read its CDF and dL/dCDF entries (barriers above): the CDF rows can take
                 // the next frame, the dL/dCDF rows the finished gradients
-                if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
+                if constexpr (!CPLX) {  // (complex: the landing rows are the output staging, see below)
+                    if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
+                }
                 // a clamped mass has no derivative (torch.where picks the constant branch)
                 const double corr_u = u_live ? (cut_scale ? dot_u + dot_v : dot_u) : 0.0;
                 const double corr_v = (!cut_scale && v_live) ? dot_v : 0.0;
@@ -860,16 +900,40 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                                  (args.upstream_scale != nullptr ? *args.upstream_scale : 1.0f);
                 const float ku = finite ? static_cast<float>(inv_u) * up * (square ? 2.0f : 1.0f) : f_nan();
                 const float kv = finite ? static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f) : f_nan();
+                if constexpr (!CPLX) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) {
-                    float ga = (bu + lsu[c]) * ku;
-                    float gb = (bv + lsv[c]) * kv;
-                    if (square) {
-                        ga *= xu[c];
-                        gb *= xv[c];
+                    for (int c = 0; c < E; ++c) {
+                        float ga = (bu + lsu[c]) * ku;
+                        float gb = (bv + lsv[c]) * kv;
+                        if (square) {
+                            ga *= xu[c];
+                            gb *= xv[c];
+                        }
+                        if (in_u || e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), ga);
+                        if (in_v || e0 + c < m) sts32(GB0 + lead_v + 4 * (e0 + c), gb);
                     }
-                    if (in_u || e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), ga);
-                    if (in_v || e0 + c < m) sts32(GB0 + lead_v + 4 * (e0 + c), gb);
+                } else {
+                    // d|z|^2/dz = 2z, d|z|/dz = z/|z| (0 at 0, like torch.abs): dL/dz = f * z, written over z.
+                    // One row at a time; if the destination's phase differs from the source's the row moves
+                    // by 8 bytes inside the landing row, so everybody reads before anybody writes.
+                    auto finish_row = [&](uint32_t raw, uint32_t stage, uint32_t lead_src, uint32_t lead_dst,
+                                          const float (&ls)[E], float base, float k, int width) {
+                        float re[E], im[E];
+#pragma unroll
+                        for (int c = 0; c < E; ++c) lds64(raw + 8 * c, re[c], im[c]);
+                        if (lead_src != lead_dst) cta_sync<TPF>();
+#pragma unroll
+                        for (int c = 0; c < E; ++c) {
+                            float f = (base + ls[c]) * k;
+                            if (!square) {
+                                const float mag = sqrtf(__fmaf_rn(re[c], re[c], __fmul_rn(im[c], im[c])));
+                                f = mag > 0.0f ? f / mag : f;  // z = 0: the gradient is 0 (torch.abs), NaN stays NaN
+                            }
+                            if (e0 + c < width) sts64(sb + stage + lead_dst + 8 * (e0 + c), f * re[c], f * im[c]);
+                        }
+                    };
+                    finish_row(rawU, STAGE_U, cur_lead_u, lead_u, lsu, bu, ku, n);
+                    finish_row(rawV, STAGE_V, cur_lead_v, lead_v, lsv, bv, kv, m);
                 }
             } else {
                 // parity harness: the rows ARE dL/dCDF, only shifted to the destination's phase
@@ -891,26 +955,35 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             cta_sync<TPF>();
             // aligned middle by bulk store, the (< 4)-float edges by plain stores
             {
-                const uint32_t head_u = min((16u - lead_u) & 15u, 4u * n);  // bytes before the aligned middle
-                const uint32_t head_v = min((16u - lead_v) & 15u, 4u * m);
-                const uint32_t body_u = (4u * n - head_u) & ~15u, body_v = (4u * m - head_v) & ~15u;
+                const uint32_t head_u = min((16u - lead_u) & 15u, 4u * wu);  // bytes before the aligned middle
+                const uint32_t head_v = min((16u - lead_v) & 15u, 4u * wv);
+                const uint32_t body_u = (4u * wu - head_u) & ~15u, body_v = (4u * wv - head_v) & ~15u;
                 if (tid == 0) {
                     if (ou != nullptr && body_u > 0)
-                        bulk_s2g(reinterpret_cast<char*>(ou) + head_u, smem + LY::A + LY::G_OFF + lead_u + head_u, body_u);
+                        bulk_s2g(reinterpret_cast<char*>(ou) + head_u, smem + STAGE_U + lead_u + head_u, body_u);
                     if (ov != nullptr && body_v > 0)
-                        bulk_s2g(reinterpret_cast<char*>(ov) + head_v, smem + LY::B + LY::G_OFF + lead_v + head_v, body_v);
+                        bulk_s2g(reinterpret_cast<char*>(ov) + head_v, smem + STAGE_V + lead_v + head_v, body_v);
                     bulk_commit();
                 }
                 if (tid < 8 && ou != nullptr) {  // threads 0-3: head floats, 4-7: tail floats
-                    const int hf = static_cast<int>(head_u >> 2), tf = n - hf - static_cast<int>(body_u >> 2);
-                    const int idx = tid < 4 ? tid : n - tf + (tid - 4);
-                    if (tid < 4 ? (tid < hf) : (tid - 4 < tf)) ou[idx] = lds32(GA0 + lead_u + 4u * idx);
+                    const int hf = static_cast<int>(head_u >> 2), tf = wu - hf - static_cast<int>(body_u >> 2);
+                    const int idx = tid < 4 ? tid : wu - tf + (tid - 4);
+                    if (tid < 4 ? (tid < hf) : (tid - 4 < tf)) ou[idx] = lds32(sb + STAGE_U + lead_u + 4u * idx);
                 }
                 if (tid >= 8 && tid < 16 && ov != nullptr) {
                     const int t8 = tid - 8;
-                    const int hf = static_cast<int>(head_v >> 2), tf = m - hf - static_cast<int>(body_v >> 2);
-                    const int idx = t8 < 4 ? t8 : m - tf + (t8 - 4);
-                    if (t8 < 4 ? (t8 < hf) : (t8 - 4 < tf)) ov[idx] = lds32(GB0 + lead_v + 4u * idx);
+                    const int hf = static_cast<int>(head_v >> 2), tf = wv - hf - static_cast<int>(body_v >> 2);
+                    const int idx = t8 < 4 ? t8 : wv - tf + (t8 - 4);
+                    if (t8 < 4 ? (t8 < hf) : (t8 - 4 < tf)) ov[idx] = lds32(sb + STAGE_V + lead_v + 4u * idx);
+                }
+                if constexpr (CPLX) {
+                    // the landing rows double as output staging: the next frame may only land once the bulk
+                    // store has read them (and the edge stores, program order of threads 0-15, are done)
+                    cta_sync<TPF>();
+                    if (tid == 0) {
+                        bulk_wait_read_all();
+                        if (next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
+                    }
                 }
             }
         }

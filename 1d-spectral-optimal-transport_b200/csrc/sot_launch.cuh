@@ -13,10 +13,10 @@ struct LaunchRequest {
     int mode;  // MODE_SPECTRA / MODE_CDF
 };
 
-template <int TPF, int E, int RS, int NCH, bool UNI, int PMODE, int OUT, int MODE>
+template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int OUT, int MODE>
 cudaError_t launch_one(const FrameArgs& a, cudaStream_t stream) {
-    auto kernel = sot_frame_kernel<TPF, E, RS, NCH, UNI, PMODE, OUT, MODE>;
-    constexpr int smem_bytes = static_cast<int>(Layout<TPF, RS, OUT, NCH, UNI>::TOTAL);
+    auto kernel = sot_frame_kernel<TPF, E, RS, NCH, UNI, CPLX, PMODE, OUT, MODE>;
+    constexpr int smem_bytes = static_cast<int>(Layout<TPF, RS, OUT, NCH, UNI, CPLX>::TOTAL);
     // per instantiation (and device): opt-in shared memory size and the persistent grid size
     static int cached_grid = 0, cached_dev = -1;
     int dev = 0;
@@ -42,21 +42,29 @@ template <int TPF, int E, int RS, int NCH, bool UNI>
 cudaError_t launch_modes(const LaunchRequest& r, cudaStream_t stream) {
     const bool p2 = (r.args.p == 2.0f);
     if (r.mode == MODE_SPECTRA) {
+        if (r.args.flags & FLAG_COMPLEX) {  // interleaved complex64 STFT rows in, complex gradient rows out
+            if (r.out == OUT_LOSS)
+                return p2 ? launch_one<TPF, E, RS, NCH, UNI, true, 2, OUT_LOSS, MODE_SPECTRA>(r.args, stream)
+                          : launch_one<TPF, E, RS, NCH, UNI, true, 0, OUT_LOSS, MODE_SPECTRA>(r.args, stream);
+            return p2 ? launch_one<TPF, E, RS, NCH, UNI, true, 2, OUT_GRAD, MODE_SPECTRA>(r.args, stream)
+                      : launch_one<TPF, E, RS, NCH, UNI, true, 0, OUT_GRAD, MODE_SPECTRA>(r.args, stream);
+        }
         if (r.out == OUT_LOSS)
-            return p2 ? launch_one<TPF, E, RS, NCH, UNI, 2, OUT_LOSS, MODE_SPECTRA>(r.args, stream)
-                      : launch_one<TPF, E, RS, NCH, UNI, 0, OUT_LOSS, MODE_SPECTRA>(r.args, stream);
-        return p2 ? launch_one<TPF, E, RS, NCH, UNI, 2, OUT_GRAD, MODE_SPECTRA>(r.args, stream)
-                  : launch_one<TPF, E, RS, NCH, UNI, 0, OUT_GRAD, MODE_SPECTRA>(r.args, stream);
+            return p2 ? launch_one<TPF, E, RS, NCH, UNI, false, 2, OUT_LOSS, MODE_SPECTRA>(r.args, stream)
+                      : launch_one<TPF, E, RS, NCH, UNI, false, 0, OUT_LOSS, MODE_SPECTRA>(r.args, stream);
+        return p2 ? launch_one<TPF, E, RS, NCH, UNI, false, 2, OUT_GRAD, MODE_SPECTRA>(r.args, stream)
+                  : launch_one<TPF, E, RS, NCH, UNI, false, 0, OUT_GRAD, MODE_SPECTRA>(r.args, stream);
     }
-    if (r.out == OUT_LOSS) return launch_one<TPF, E, RS, NCH, UNI, 0, OUT_LOSS, MODE_CDF>(r.args, stream);
-    return launch_one<TPF, E, RS, NCH, UNI, 0, OUT_GRAD, MODE_CDF>(r.args, stream);
+    if (r.out == OUT_LOSS) return launch_one<TPF, E, RS, NCH, UNI, false, 0, OUT_LOSS, MODE_CDF>(r.args, stream);
+    return launch_one<TPF, E, RS, NCH, UNI, false, 0, OUT_GRAD, MODE_CDF>(r.args, stream);
 }
 
 template <int TPF, int E, int RS, int NCH>
 cudaError_t launch_config(const LaunchRequest& r, cudaStream_t stream) {
     if (r.out == OUT_PLAN)  // the plan emitter reads positions: general kernel only
-        return r.mode == MODE_SPECTRA ? launch_one<TPF, E, RS, NCH, false, 0, OUT_PLAN, MODE_SPECTRA>(r.args, stream)
-                                      : launch_one<TPF, E, RS, NCH, false, 0, OUT_PLAN, MODE_CDF>(r.args, stream);
+        return r.mode == MODE_SPECTRA
+                   ? launch_one<TPF, E, RS, NCH, false, false, 0, OUT_PLAN, MODE_SPECTRA>(r.args, stream)
+                   : launch_one<TPF, E, RS, NCH, false, false, 0, OUT_PLAN, MODE_CDF>(r.args, stream);
     const FrameArgs& a = r.args;
     const bool uniform = (a.flags & FLAG_UNIFORM) && a.pos_u_stride == 0 && a.pos_v_stride == 0 && a.n >= 2;
     return uniform ? launch_modes<TPF, E, RS, NCH, true>(r, stream) : launch_modes<TPF, E, RS, NCH, false>(r, stream);

@@ -55,12 +55,19 @@ class _SotFrames(torch.autograd.Function):
         grad_loss = grad_loss.contiguous().float()
         if ctx.mode == "fused":
             gu, gv = ctx.saved_tensors
-            gu = _capi.scale_rows(gu, grad_loss) if need_u else None
-            gv = _capi.scale_rows(gv, grad_loss) if need_v else None
+            gu = _scale_rows(gu, grad_loss) if need_u else None
+            gv = _scale_rows(gv, grad_loss) if need_v else None
         else:
             u, v, pos_u, pos_v = ctx.saved_tensors
             _, gu, gv = _capi.forward_backward(u, v, pos_u, pos_v, ctx.p, ctx.flags, grad_loss, False, need_u, need_v)
         return gu, gv, None, None, None, None, None
+
+
+def _scale_rows(unit: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    if not unit.is_complex():
+        return _capi.scale_rows(unit, scale)
+    flat = torch.view_as_real(unit).reshape(unit.shape[0], -1)  # (N, 2F) interleaved
+    return torch.view_as_complex(_capi.scale_rows(flat, scale).reshape(unit.shape[0], -1, 2))
 
 
 # --------------------------------------------------------------------------------------
@@ -70,14 +77,17 @@ _sorted_cache: dict = {}  # id(user tensor) -> (weakref, version, ascending?)
 
 
 def _rows(t: torch.Tensor, name: str) -> torch.Tensor:
-    """(B, T, F) or (N, F) -> contiguous float32 (N, F) (losses.py:158-165)."""
+    """(B, T, F) or (N, F) -> contiguous float32 (N, F) (losses.py:158-165).
+
+    complex64 rows (an STFT that has not been through `.abs()`, features.py:236) are kept complex:
+    the kernels form the magnitude themselves and return complex gradients."""
     if not t.is_cuda:
         raise _capi.SotError(f"sot_b200: `{name}` lives on {t.device}; the SOT kernels are CUDA only "
                              "(no CPU fallback exists by design)")
     if t.dtype in (torch.float16, torch.bfloat16):
         t = t.float()
-    elif t.dtype != torch.float32:
-        raise TypeError(f"sot_b200: `{name}` must be float32 (or half/bfloat16, upcast), got {t.dtype}")
+    elif t.dtype not in (torch.float32, torch.complex64):
+        raise TypeError(f"sot_b200: `{name}` must be float32 (or half/bfloat16, upcast) or complex64, got {t.dtype}")
     if t.ndim == 3:
         t = t.reshape(-1, t.shape[-1])
     elif t.ndim != 2:
@@ -178,6 +188,10 @@ def _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_
     """Reference prologue that stays on the host: flatten, canonicalise supports, hoisted sort."""
     assert p >= 1, f"The OT loss is only valid for p>=1, {p} was given"  # losses.py:271
     u, v = _rows(x, "x"), _rows(y, "y")
+    if u.is_complex() != v.is_complex():  # one side already a magnitude: take |.| of the other in torch
+        u, v = (u.abs() if u.is_complex() else u), (v.abs() if v.is_complex() else v)
+    if u.is_complex() and raw_weights:
+        raise TypeError("sot_b200: `wasserstein_1d` weights must be real")
     if u.shape[0] != v.shape[0]:
         raise ValueError(f"sot_b200: x has {u.shape[0]} frames, y has {v.shape[0]}")
     pu, pv = _support(x_pos, u, "x_pos"), _support(y_pos, v, "y_pos")
@@ -313,6 +327,7 @@ class Wasserstein1D(torch.nn.Module):
 
 
 def _quantiles(x, y, x_pos, y_pos, square, cut_scale, require_sort, raw_weights=False):
+    x, y = (x.abs() if x.is_complex() else x), (y.abs() if y.is_complex() else y)  # metrics path: plain |.|
     u, v = _rows(x.detach(), "x"), _rows(y.detach(), "y")
     pu, pv = _support(x_pos, u, "x_pos"), _support(y_pos, v, "y_pos")
     sort_u, sort_v = require_sort if isinstance(require_sort, tuple) else (require_sort, require_sort)

@@ -40,6 +40,12 @@ extern "C" {
                              trainer.py:193-197).  Positions are then computed, not loaded: same bits,
                              fewer shared-memory accesses.  Ignored by sot_quantiles_device. */
 
+#define SOT_COMPLEX_INPUT 32 /* fused STFT-magnitude prologue (features.py:104-110, 217-237): u, v are rows of
+                              interleaved complex64 STFT bins [N, n_u] / [N, n_v] (2 floats per bin, e.g.
+                              `torch.stft(..., return_complex=True)` transposed to frame-major), the
+                              magnitude is formed in the kernel, and grad_u / grad_v are complex rows
+                              (dL/dre, dL/dim) of the same layout.  Forward / forward+backward entries only. */
+
 /* error codes */
 #define SOT_OK 0
 #define SOT_EINVAL (-1)   /* bad pointer / size / flag combination        */
@@ -59,7 +65,7 @@ typedef struct sot_problem {
     int64_t pos_u_stride;  /*   of a [N, n_*] array with this element stride                */
     int64_t pos_v_stride;
     float p;               /* order of the distance, >= 1 (result is W_p^p, no root)        */
-    int32_t flags;         /* SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS | SOT_UNIFORM_GRID */
+    int32_t flags;         /* SOT_SQUARE | SOT_CUT_SCALE | SOT_LIMIT | SOT_RAW_WEIGHTS | SOT_UNIFORM_GRID | SOT_COMPLEX_INPUT */
 } sot_problem;
 
 /* ---- the hot path ------------------------------------------------------------------------- */
