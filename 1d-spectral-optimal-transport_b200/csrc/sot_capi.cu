@@ -161,6 +161,8 @@ sot::FrameArgs base_args(const sot_problem* p) {
 int launch(const sot_problem* p, sot::LaunchRequest& r, void* stream) {
     if ((p->flags & SOT_COMPLEX_INPUT) && (r.mode != sot::MODE_SPECTRA || r.out == sot::OUT_PLAN))
         return fail(SOT_EINVAL, "SOT_COMPLEX_INPUT is only valid for the forward / forward+backward entry points");
+    if ((p->flags & SOT_COMPLEX_INPUT) && (p->flags & SOT_RAW_WEIGHTS))
+        return fail(SOT_EINVAL, "SOT_RAW_WEIGHTS rows are real weights, not complex spectra");
     if (p->n_frames == 0) return SOT_OK;
     const Config* c = pick_config(p->n_u, p->n_v);
     if (c == nullptr)

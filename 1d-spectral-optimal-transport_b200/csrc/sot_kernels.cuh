@@ -54,6 +54,8 @@ enum : int {
 
 enum : int {
     MODE_SPECTRA = 0,  // inputs are magnitudes: full prologue
+    MODE_RAW = 2,      // inputs are weights used as given (FLAG_RAW): no normalisation, CDF = cumsum with fp64
+                       // accumulation exactly like the reference's (see stage 2)
     MODE_CDF = 1,      // inputs are CDF rows (parity harness): skip the prologue; with grads the
                        // outputs are dL/dcu, dL/dcv (no suffix scan / chain rule)
 };
@@ -149,6 +151,32 @@ SOT_DEVINL void lds64(uint32_t a, float& x, float& y) {
 SOT_DEVINL void sts64(uint32_t a, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two lanes per issued instruction).
+// The kernel is bound by instruction issue, so everything that is elementwise on (u, v) bin pairs
+// -- squares, local prefix sums, CDF scaling, the gradient chain rule -- runs on pairs.
+using f32x2 = unsigned long long;
+SOT_DEVINL f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+SOT_DEVINL void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+SOT_DEVINL f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+SOT_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+SOT_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // One merge step's advance: the consumed side (v if b < a, else u: u first on equal values, the
 // stable order of `cat(cu, cv)`) gets its next CDF entry and that entry's position.  ONE load per
 // array from the SELECTED address: a pair of predicated loads (one per side, half the lanes each)
@@ -223,38 +251,63 @@ SOT_DEVINL void cta_sync() {
     }
 }
 
-// Exclusive scan (prefix; suffix when REVERSE) of one fp64 value over the TPF threads of the CTA.
+// Exclusive scan (prefix; suffix when REVERSE) of fp64 values over the TPF threads of the CTA.
 // Contains one CTA barrier when the CTA has more than one warp.
+// Two scans at once (one barrier): `slot` holds 2 * NW doubles.  a, b: in = my value, out = exclusive
+// prefix; inc_a, inc_b = inclusive prefix, BITWISE equal to the next thread's exclusive prefix (same
+// operands, same additions), which the CDF stage relies on.
 template <int TPF, bool REVERSE>
-SOT_DEVINL void cta_scan1(double& a, double& total, double* slot, int tid) {
+SOT_DEVINL void cta_scan2(double& a, double& b, double& inc_a, double& inc_b, double& total_a, double& total_b,
+                          double* slot, int tid) {
     constexpr int NW = TPF / 32;
     const int lane = tid & 31, w = tid >> 5;
-    double ia = a;
+    double ia = a, ib = b;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const double ya = REVERSE ? __shfl_down_sync(FULL_MASK, ia, off) : __shfl_up_sync(FULL_MASK, ia, off);
+        const double yb = REVERSE ? __shfl_down_sync(FULL_MASK, ib, off) : __shfl_up_sync(FULL_MASK, ib, off);
         const bool ok = REVERSE ? (lane + off < 32) : (lane >= off);
-        if (ok) ia += ya;
+        if (ok) {
+            ia += ya;
+            ib += yb;
+        }
     }
     double ea = REVERSE ? __shfl_down_sync(FULL_MASK, ia, 1) : __shfl_up_sync(FULL_MASK, ia, 1);
-    if (lane == (REVERSE ? 31 : 0)) ea = 0.0;
+    double eb = REVERSE ? __shfl_down_sync(FULL_MASK, ib, 1) : __shfl_up_sync(FULL_MASK, ib, 1);
+    if (lane == (REVERSE ? 31 : 0)) ea = eb = 0.0;
     const double wa = __shfl_sync(FULL_MASK, ia, REVERSE ? 0 : 31);
+    const double wb = __shfl_sync(FULL_MASK, ib, REVERSE ? 0 : 31);
     if constexpr (NW == 1) {
         a = ea;
-        total = wa;
+        b = eb;
+        inc_a = ia;
+        inc_b = ib;
+        total_a = wa;
+        total_b = wb;
     } else {
-        if (lane == 0) slot[w] = wa;
+        if (lane == 0) {
+            slot[w] = wa;
+            slot[NW + w] = wb;
+        }
         __syncthreads();
-        double pa = 0.0, ta = 0.0;
+        double pa = 0.0, ta = 0.0, pb = 0.0, tb = 0.0;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
             const int kk = REVERSE ? (NW - 1 - k) : k;
-            const double sa = slot[kk];
-            if (REVERSE ? (kk > w) : (kk < w)) pa = ta + sa;
+            const double sa = slot[kk], sb = slot[NW + kk];
+            if (REVERSE ? (kk > w) : (kk < w)) {
+                pa = ta + sa;
+                pb = tb + sb;
+            }
             ta += sa;
+            tb += sb;
         }
         a = pa + ea;
-        total = ta;
+        b = pb + eb;
+        inc_a = pa + ia;
+        inc_b = pb + ib;
+        total_a = ta;
+        total_b = tb;
     }
 }
 
@@ -300,6 +353,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     static_assert(NCH == 1 || NCH == 2, "one or two merge chains per thread");
     static_assert(!(UNI && OUT == OUT_PLAN), "the plan emitter always reads positions");
     static_assert(!CPLX || (MODE == MODE_SPECTRA && OUT != OUT_PLAN), "complex input: loss / gradient from spectra only");
+    constexpr bool FROM_BINS = (MODE != MODE_CDF);  // spectra or raw weights: the kernel builds the CDFs
     using LY = Layout<TPF, RS, OUT, NCH, UNI, CPLX>;
     constexpr int CW = CPLX ? 2 : 1;  // floats per raw bin
     constexpr int NCHUNK = NCH * TPF;
@@ -433,87 +487,103 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
 
         // ---- stages 1 + 2: blocked read of my E bins (conflict free: E is odd), masses and CDFs
         //      (fp64 accumulation, one rounding to fp32 per entry) ---------------------------------------
-        if constexpr (MODE == MODE_SPECTRA) {
-            double P[E];
-            double tot_u, tot_v;
-            {
-                double t = 0.0;
+        if constexpr (FROM_BINS) {
+            // Pass 1: my E (u, v) bin pairs -> values to accumulate (x, x^2, |z| or |z|^2) and their local
+            // sums, in packed fp32.  The per-thread sums T are then scanned across the CTA in fp64.
 #pragma unroll
-                for (int c = 0; c < E; ++c) {  // (past the row: finite garbage inside the landing rows)
-                    if constexpr (CPLX) {  // |z|^2 = re^2 + im^2 directly (no square root), or |z|
-                        float re, im;
-                        lds64(rawU + 8 * c, re, im);
-                        const float s2 = __fmaf_rn(re, re, __fmul_rn(im, im));
-                        xu[c] = square ? s2 : sqrtf(s2);
-                    } else {
-                        xu[c] = lds32(rawU + 4 * c);
-                    }
-                }
-                if (!in_u) {
-#pragma unroll
-                    for (int c = 0; c < E; ++c) xu[c] = (e0 + c < n) ? xu[c] : 0.0f;
-                }
-#pragma unroll
-                for (int c = 0; c < E; ++c) {
-                    t += static_cast<double>((square && !CPLX) ? xu[c] * xu[c] : xu[c]);
-                    P[c] = t;
-                }
-                double off = t;
-                cta_scan1<TPF, false>(off, tot_u, scratch, tid);  // (its barrier also orders raw reads before CDF writes)
-                const float mass_u = static_cast<float>(tot_u);
-                u_live = mass_u > SAFE_EPS;  // utils.py:137: den <= eps -> eps
-                inv_u = recip_f64(u_live ? mass_u : SAFE_EPS);
-                if (args.flags & FLAG_RAW) inv_u = 1.0;
-                if constexpr (NW == 1) __syncwarp();
-                if (in_u) {
-#pragma unroll
-                    for (int c = 0; c < E; ++c) sts32(A0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_u));
+            for (int c = 0; c < E; ++c) {  // (past the row: finite garbage inside the landing rows)
+                if constexpr (CPLX) {  // |z|^2 = re^2 + im^2 directly (no square root), or |z|
+                    float re, im;
+                    lds64(rawU + 8 * c, re, im);
+                    const float s2 = __fmaf_rn(re, re, __fmul_rn(im, im));
+                    xu[c] = square ? s2 : sqrtf(s2);
+                    lds64(rawV + 8 * c, re, im);
+                    const float t2 = __fmaf_rn(re, re, __fmul_rn(im, im));
+                    xv[c] = square ? t2 : sqrtf(t2);
                 } else {
-#pragma unroll
-                    for (int c = 0; c < E; ++c)
-                        if (e0 + c < n) sts32(A0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_u));
+                    xu[c] = lds32(rawU + 4 * c);
+                    xv[c] = lds32(rawV + 4 * c);
                 }
             }
-            {
-                double t = 0.0;
+            if (!in_u) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) xu[c] = (e0 + c < n) ? xu[c] : 0.0f;
+            }
+            if (!in_v) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) xv[c] = (e0 + c < m) ? xv[c] : 0.0f;
+            }
+            const bool sq = square && !CPLX;
+            // Weights used as given (module-level `wasserstein_1d`, FLAG_RAW): the CDF is a plain cumsum, which
+            // the reference accumulates in fp64 -- reproduced exactly, because with a handful of atoms the strict
+            // `qs > 1` mask decides over a whole atom on the last ulp of the CDF.  Normalised spectra (every
+            // `Wasserstein1D` call) take the packed fp32 route: a few ulp, at a third of the instructions.
+            constexpr bool exact = (MODE == MODE_RAW);
+            double off_u, off_v, inc_u, inc_v, tot_u, tot_v;
+            if constexpr (exact) {
+                off_u = off_v = 0.0;
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    if constexpr (CPLX) {
-                        float re, im;
-                        lds64(rawV + 8 * c, re, im);
-                        const float s2 = __fmaf_rn(re, re, __fmul_rn(im, im));
-                        xv[c] = square ? s2 : sqrtf(s2);
-                    } else {
-                        xv[c] = lds32(rawV + 4 * c);
-                    }
+                    off_u += static_cast<double>(sq ? xu[c] * xu[c] : xu[c]);
+                    off_v += static_cast<double>(sq ? xv[c] * xv[c] : xv[c]);
                 }
-                if (!in_v) {
-#pragma unroll
-                    for (int c = 0; c < E; ++c) xv[c] = (e0 + c < m) ? xv[c] : 0.0f;
-                }
+            } else {
+                f32x2 t2 = 0;
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    t += static_cast<double>((square && !CPLX) ? xv[c] * xv[c] : xv[c]);
-                    P[c] = t;
+                    const f32x2 x2 = pack2(xu[c], xv[c]);
+                    t2 = sq ? fma2(x2, x2, t2) : add2(t2, x2);  // (the same instruction as in pass 2: T is its last prefix)
                 }
-                double off = t;
-                cta_scan1<TPF, false>(off, tot_v, scratch + NW, tid);
-                const float mass_v = static_cast<float>(tot_v);
-                v_live = mass_v > SAFE_EPS;
-                inv_v = cut_scale ? inv_u : recip_f64(v_live ? mass_v : SAFE_EPS);
-                if (args.flags & FLAG_RAW) {  // no normalisation, hence no mass term in the gradient
-                    inv_v = 1.0;
-                    u_live = v_live = false;
-                }
-                if constexpr (NW == 1) __syncwarp();
-                if (in_v) {
+                float Tu, Tv;
+                unpack2(t2, Tu, Tv);
+                off_u = static_cast<double>(Tu);
+                off_v = static_cast<double>(Tv);
+            }
+            cta_scan2<TPF, false>(off_u, off_v, inc_u, inc_v, tot_u, tot_v, scratch, tid);  // (its barrier also orders raw reads before CDF writes)
+            const float mass_u = static_cast<float>(tot_u), mass_v = static_cast<float>(tot_v);
+            u_live = mass_u > SAFE_EPS;  // utils.py:137: den <= eps -> eps
+            v_live = mass_v > SAFE_EPS;
+            inv_u = recip_f64(u_live ? mass_u : SAFE_EPS);
+            inv_v = cut_scale ? inv_u : recip_f64(v_live ? mass_v : SAFE_EPS);
+            if constexpr (exact) {  // no normalisation, hence no mass term in the gradient
+                inv_u = inv_v = 1.0;
+                u_live = v_live = false;
+            }
+            if constexpr (NW == 1) __syncwarp();
+            // Pass 2: CDF entry = base + (local prefix) * 1/mass with base = (sum of the threads before
+            // me) * 1/mass from the fp64 scan, split into an fp32 head and tail so that the one rounding that
+            // matters is the final add.  The local prefix is the SAME fp32 sequence as in pass 1, so the entry
+            // after my last bin is exactly the next thread's base; each entry is capped by that value, which
+            // keeps the row non-decreasing across thread boundaries whatever the roundings of the scaling do.
+            if constexpr (exact) {
+                double tu = off_u, tv = off_v;
 #pragma unroll
-                    for (int c = 0; c < E; ++c) sts32(B0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_v));
-                } else {
-#pragma unroll
-                    for (int c = 0; c < E; ++c)
-                        if (e0 + c < m) sts32(B0 + 4 * (e0 + c), static_cast<float>((off + P[c]) * inv_v));
+                for (int c = 0; c < E; ++c) {
+                    tu += static_cast<double>(sq ? xu[c] * xu[c] : xu[c]);
+                    tv += static_cast<double>(sq ? xv[c] * xv[c] : xv[c]);
+                    if (in_u || e0 + c < n) sts32(A0 + 4 * (e0 + c), static_cast<float>(tu * inv_u));
+                    if (in_v || e0 + c < m) sts32(B0 + 4 * (e0 + c), static_cast<float>(tv * inv_v));
                 }
+            } else {
+            const double base_u = off_u * inv_u, base_v = off_v * inv_v;
+            const float bh_u = static_cast<float>(base_u), bh_v = static_cast<float>(base_v);
+            const float bl_u = static_cast<float>(base_u - static_cast<double>(bh_u));
+            const float bl_v = static_cast<float>(base_v - static_cast<double>(bh_v));
+            const float cap_u = static_cast<float>(inc_u * inv_u), cap_v = static_cast<float>(inc_v * inv_v);
+            const f32x2 bh2 = pack2(bh_u, bh_v), bl2 = pack2(bl_u, bl_v);
+            const f32x2 inv2 = pack2(static_cast<float>(inv_u), static_cast<float>(inv_v));
+            f32x2 p2 = 0;
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const f32x2 x2 = pack2(xu[c], xv[c]);
+                p2 = sq ? fma2(x2, x2, p2) : add2(p2, x2);
+                float ca, cb;
+                unpack2(add2(fma2(p2, inv2, bl2), bh2), ca, cb);
+                ca = fminf(ca, cap_u);
+                cb = fminf(cb, cap_v);
+                if (in_u || e0 + c < n) sts32(A0 + 4 * (e0 + c), ca);
+                if (in_v || e0 + c < m) sts32(B0 + 4 * (e0 + c), cb);
+            }
             }
             // NaN / inf anywhere (or an overflowing cut-mode scale) poisons the frame: the walk is skipped
             // (its +inf sentinels must stay unique) and NaN is written instead
@@ -840,30 +910,36 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             // staging rows of the output: the dL/dCDF rows, or (complex) the landing rows, rewritten in place
             constexpr uint32_t STAGE_U = CPLX ? LY::LAND : LY::A + LY::G_OFF;
             constexpr uint32_t STAGE_V = CPLX ? LY::LAND + LY::LAND_ROW : LY::B + LY::G_OFF;
-            if constexpr (MODE == MODE_SPECTRA) {
+            if constexpr (FROM_BINS) {
                 // cumsum transpose (suffix sums of dL/dCDF) and the normalisation chain rule.
                 // sum_i gw_i w_i = sum_i (dL/dc_i) c_i (Abel summation), so the mass term needs only the
                 // CDF values and dL/dCDF that are already in shared memory.
-                float lsu[E], lsv[E];
-                float su = 0.0f, sv = 0.0f, du = 0.0f, dv = 0.0f;
+                // (packed fp32 on (u, v) pairs, like the CDF stage)
+                f32x2 ls2[E];
+                f32x2 s2 = 0, d2 = 0;
 #pragma unroll
                 for (int c = E - 1; c >= 0; --c) {
+                    float gu = 0.0f, gv = 0.0f, cu = 0.0f, cv = 0.0f;
                     if (in_u || e0 + c < n) {
-                        const float gq = lds32(GA0 + 4 * (e0 + c));
-                        su += gq;
-                        du = fmaf(gq, lds32(A0 + 4 * (e0 + c)), du);
+                        gu = lds32(GA0 + 4 * (e0 + c));
+                        cu = lds32(A0 + 4 * (e0 + c));
                     }
-                    lsu[c] = su;
                     if (in_v || e0 + c < m) {
-                        const float gq = lds32(GB0 + 4 * (e0 + c));
-                        sv += gq;
-                        dv = fmaf(gq, lds32(B0 + 4 * (e0 + c)), dv);
+                        gv = lds32(GB0 + 4 * (e0 + c));
+                        cv = lds32(B0 + 4 * (e0 + c));
                     }
-                    lsv[c] = sv;
+                    const f32x2 g2 = pack2(gu, gv);
+                    s2 = add2(s2, g2);
+                    d2 = fma2(g2, pack2(cu, cv), d2);
+                    ls2[c] = s2;
                 }
-                double off_u = static_cast<double>(su), off_v = static_cast<double>(sv), tu, tv;
-                cta_scan1<TPF, true>(off_u, tu, scratch + 4 * NW, tid);
-                cta_scan1<TPF, true>(off_v, tv, scratch + 5 * NW, tid);
+                float su, sv, du, dv;
+                unpack2(s2, su, sv);
+                unpack2(d2, du, dv);
+                double off_u = static_cast<double>(su), off_v = static_cast<double>(sv), iu_, iv_, tu, tv;
+                cta_scan2<TPF, true>(off_u, off_v, iu_, iv_, tu, tv, scratch + 4 * NW, tid);
+                (void)iu_;
+                (void)iv_;
                 double dot_u = static_cast<double>(du), dot_v = static_cast<double>(dv);
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -901,14 +977,13 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 const float ku = finite ? static_cast<float>(inv_u) * up * (square ? 2.0f : 1.0f) : f_nan();
                 const float kv = finite ? static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f) : f_nan();
                 if constexpr (!CPLX) {
+                    const f32x2 b2 = pack2(bu, bv), k2 = pack2(ku, kv);
 #pragma unroll
                     for (int c = 0; c < E; ++c) {
-                        float ga = (bu + lsu[c]) * ku;
-                        float gb = (bv + lsv[c]) * kv;
-                        if (square) {
-                            ga *= xu[c];
-                            gb *= xv[c];
-                        }
+                        f32x2 g2 = mul2(add2(b2, ls2[c]), k2);
+                        if (square) g2 = mul2(g2, pack2(xu[c], xv[c]));
+                        float ga, gb;
+                        unpack2(g2, ga, gb);
                         if (in_u || e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), ga);
                         if (in_v || e0 + c < m) sts32(GB0 + lead_v + 4 * (e0 + c), gb);
                     }
@@ -916,6 +991,9 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     // d|z|^2/dz = 2z, d|z|/dz = z/|z| (0 at 0, like torch.abs): dL/dz = f * z, written over z.
                     // One row at a time; if the destination's phase differs from the source's the row moves
                     // by 8 bytes inside the landing row, so everybody reads before anybody writes.
+                    float lsu[E], lsv[E];
+#pragma unroll
+                    for (int c = 0; c < E; ++c) unpack2(ls2[c], lsu[c], lsv[c]);
                     auto finish_row = [&](uint32_t raw, uint32_t stage, uint32_t lead_src, uint32_t lead_dst,
                                           const float (&ls)[E], float base, float k, int width) {
                         float re[E], im[E];

