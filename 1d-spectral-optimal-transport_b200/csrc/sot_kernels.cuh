@@ -161,6 +161,23 @@ SOT_DEVINL f32x2 pack2(float lo, float hi) {
     return r;
 }
 SOT_DEVINL void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// (lo, hi) = (shared[a], shared[b]): the loads define the two halves of the pair directly
+SOT_DEVINL f32x2 lds32x2(uint32_t a, uint32_t b) {
+    f32x2 r;
+    asm volatile("{\n .reg .f32 lo, hi;\n ld.shared.f32 lo, [%1];\n ld.shared.f32 hi, [%2];\n mov.b64 %0, {lo, hi};\n}"
+                 : "=l"(r)
+                 : "r"(a), "r"(b));
+    return r;
+}
+// (keep_lo ? lo : 0, keep_hi ? hi : 0)
+SOT_DEVINL f32x2 mask2(f32x2 v, bool keep_lo, bool keep_hi) {
+    f32x2 r;
+    asm("{\n .reg .f32 lo, hi;\n .reg .pred p, q;\n mov.b64 {lo, hi}, %1;\n setp.ne.s32 p, %2, 0;\n setp.ne.s32 q, %3, 0;\n"
+        " selp.f32 lo, lo, 0f00000000, p;\n selp.f32 hi, hi, 0f00000000, q;\n mov.b64 %0, {lo, hi};\n}"
+        : "=l"(r)
+        : "l"(v), "r"(static_cast<int>(keep_lo)), "r"(static_cast<int>(keep_hi)));
+    return r;
+}
 SOT_DEVINL f32x2 add2(f32x2 a, f32x2 b) {
     f32x2 r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -251,37 +268,128 @@ SOT_DEVINL void cta_sync() {
     }
 }
 
-// Exclusive scan (prefix; suffix when REVERSE) of fp64 values over the TPF threads of the CTA.
-// Contains one CTA barrier when the CTA has more than one warp.
-// Two scans at once (one barrier): `slot` holds 2 * NW doubles.  a, b: in = my value, out = exclusive
-// prefix; inc_a, inc_b = inclusive prefix, BITWISE equal to the next thread's exclusive prefix (same
-// operands, same additions), which the CDF stage relies on.
-template <int TPF, bool REVERSE>
-SOT_DEVINL void cta_scan2(double& a, double& b, double& inc_a, double& inc_b, double& total_a, double& total_b,
-                          double* slot, int tid) {
+// One Hillis-Steele step of a warp scan of an fp64 value: two 32-bit shuffles whose "source lane in range"
+// predicate guards the add (what the compiler makes of __shfl_up_sync(double) costs three times as much).
+template <bool REVERSE, int OFF>
+SOT_DEVINL void scan_step(double& v) {
+    if constexpr (REVERSE) {
+        asm volatile(
+            "{\n .reg .b32 lo, hi, ylo, yhi;\n .reg .f64 y;\n .reg .pred p;\n"
+            " mov.b64 {lo, hi}, %0;\n"
+            " shfl.sync.down.b32 ylo|p, lo, %1, 0x1f, 0xffffffff;\n"
+            " shfl.sync.down.b32 yhi, hi, %1, 0x1f, 0xffffffff;\n"
+            " mov.b64 y, {ylo, yhi};\n"
+            " @p add.f64 %0, %0, y;\n}"
+            : "+d"(v)
+            : "n"(OFF));
+    } else {
+        asm volatile(
+            "{\n .reg .b32 lo, hi, ylo, yhi;\n .reg .f64 y;\n .reg .pred p;\n"
+            " mov.b64 {lo, hi}, %0;\n"
+            " shfl.sync.up.b32 ylo|p, lo, %1, 0x0, 0xffffffff;\n"
+            " shfl.sync.up.b32 yhi, hi, %1, 0x0, 0xffffffff;\n"
+            " mov.b64 y, {ylo, yhi};\n"
+            " @p add.f64 %0, %0, y;\n}"
+            : "+d"(v)
+            : "n"(OFF));
+    }
+}
+// Exclusive scans (prefix; suffix when REVERSE) over the TPF threads of the CTA of two fp32 values, carried
+// in fp64.  ta, tb: my values; returns my exclusive offsets and the CTA totals.  One CTA barrier when the
+// CTA has more than one warp; `slot` holds 2 * NW doubles.
+// nxt_a / nxt_b = the exclusive offset of the NEXT thread (the CTA total for the last one), bitwise: the
+// CDF stage caps my entries with it.
+template <int TPF, bool REVERSE, bool WANT_NEXT>
+SOT_DEVINL void cta_scan2(float ta, float tb, double& off_a, double& off_b, double& nxt_a, double& nxt_b,
+                          double& total_a, double& total_b, double* slot, int tid) {
+    constexpr int NW = TPF / 32;
+    const int lane = tid & 31, w = tid >> 5;
+    const int edge = REVERSE ? 31 : 0;  // the lane with nothing before it
+    // shift by one lane first: the inclusive scan of the shifted values is the exclusive scan
+    float sa = REVERSE ? __shfl_down_sync(FULL_MASK, ta, 1) : __shfl_up_sync(FULL_MASK, ta, 1);
+    float sb = REVERSE ? __shfl_down_sync(FULL_MASK, tb, 1) : __shfl_up_sync(FULL_MASK, tb, 1);
+    double ea = lane == edge ? 0.0 : static_cast<double>(sa);
+    double eb = lane == edge ? 0.0 : static_cast<double>(sb);
+    scan_step<REVERSE, 1>(ea);
+    scan_step<REVERSE, 1>(eb);
+    scan_step<REVERSE, 2>(ea);
+    scan_step<REVERSE, 2>(eb);
+    scan_step<REVERSE, 4>(ea);
+    scan_step<REVERSE, 4>(eb);
+    scan_step<REVERSE, 8>(ea);
+    scan_step<REVERSE, 8>(eb);
+    scan_step<REVERSE, 16>(ea);
+    scan_step<REVERSE, 16>(eb);
+    // warp totals, formed on the last lane of the scan direction
+    const double wa_mine = ea + static_cast<double>(ta), wb_mine = eb + static_cast<double>(tb);
+    if constexpr (NW == 1) {
+        off_a = ea;
+        off_b = eb;
+        total_a = __shfl_sync(FULL_MASK, wa_mine, 31 - edge);
+        total_b = __shfl_sync(FULL_MASK, wb_mine, 31 - edge);
+        if constexpr (WANT_NEXT) {
+            const double na = REVERSE ? __shfl_up_sync(FULL_MASK, ea, 1) : __shfl_down_sync(FULL_MASK, ea, 1);
+            const double nb = REVERSE ? __shfl_up_sync(FULL_MASK, eb, 1) : __shfl_down_sync(FULL_MASK, eb, 1);
+            nxt_a = lane == 31 - edge ? total_a : na;
+            nxt_b = lane == 31 - edge ? total_b : nb;
+        }
+    } else {
+        if (lane == 31 - edge) {
+            slot[w] = wa_mine;
+            slot[NW + w] = wb_mine;
+        }
+        __syncthreads();
+        double pa = 0.0, pb = 0.0, qa = 0.0, qb = 0.0, xa = 0.0, xb = 0.0;  // prefix before my warp, through my warp, total
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int kk = REVERSE ? (NW - 1 - k) : k;
+            const double va = slot[kk], vb = slot[NW + kk];
+            if (REVERSE ? (kk > w) : (kk < w)) {
+                pa = xa + va;
+                pb = xb + vb;
+            }
+            xa += va;
+            xb += vb;
+            if (kk == w) {
+                qa = xa;
+                qb = xb;
+            }
+        }
+        off_a = pa + ea;
+        off_b = pb + eb;
+        total_a = xa;
+        total_b = xb;
+        if constexpr (WANT_NEXT) {
+            // next thread in my warp: its offset is pa + (its ea), the same addition it performs itself; across
+            // the warp boundary: the next warp's pa is exactly qa (same sequence of additions), plus its ea = 0
+            const double na = REVERSE ? __shfl_up_sync(FULL_MASK, off_a, 1) : __shfl_down_sync(FULL_MASK, off_a, 1);
+            const double nb = REVERSE ? __shfl_up_sync(FULL_MASK, off_b, 1) : __shfl_down_sync(FULL_MASK, off_b, 1);
+            nxt_a = lane == 31 - edge ? qa : na;
+            nxt_b = lane == 31 - edge ? qb : nb;
+        }
+    }
+}
+
+// The same for two fp64 values (raw-weights mode, not a hot path): a, b in = my value, out = exclusive offset.
+template <int TPF>
+SOT_DEVINL void cta_scan2d(double& a, double& b, double& total_a, double& total_b, double* slot, int tid) {
     constexpr int NW = TPF / 32;
     const int lane = tid & 31, w = tid >> 5;
     double ia = a, ib = b;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        const double ya = REVERSE ? __shfl_down_sync(FULL_MASK, ia, off) : __shfl_up_sync(FULL_MASK, ia, off);
-        const double yb = REVERSE ? __shfl_down_sync(FULL_MASK, ib, off) : __shfl_up_sync(FULL_MASK, ib, off);
-        const bool ok = REVERSE ? (lane + off < 32) : (lane >= off);
-        if (ok) {
+        const double ya = __shfl_up_sync(FULL_MASK, ia, off), yb = __shfl_up_sync(FULL_MASK, ib, off);
+        if (lane >= off) {
             ia += ya;
             ib += yb;
         }
     }
-    double ea = REVERSE ? __shfl_down_sync(FULL_MASK, ia, 1) : __shfl_up_sync(FULL_MASK, ia, 1);
-    double eb = REVERSE ? __shfl_down_sync(FULL_MASK, ib, 1) : __shfl_up_sync(FULL_MASK, ib, 1);
-    if (lane == (REVERSE ? 31 : 0)) ea = eb = 0.0;
-    const double wa = __shfl_sync(FULL_MASK, ia, REVERSE ? 0 : 31);
-    const double wb = __shfl_sync(FULL_MASK, ib, REVERSE ? 0 : 31);
+    double ea = __shfl_up_sync(FULL_MASK, ia, 1), eb = __shfl_up_sync(FULL_MASK, ib, 1);
+    if (lane == 0) ea = eb = 0.0;
+    const double wa = __shfl_sync(FULL_MASK, ia, 31), wb = __shfl_sync(FULL_MASK, ib, 31);
     if constexpr (NW == 1) {
         a = ea;
         b = eb;
-        inc_a = ia;
-        inc_b = ib;
         total_a = wa;
         total_b = wb;
     } else {
@@ -290,24 +398,21 @@ SOT_DEVINL void cta_scan2(double& a, double& b, double& inc_a, double& inc_b, do
             slot[NW + w] = wb;
         }
         __syncthreads();
-        double pa = 0.0, ta = 0.0, pb = 0.0, tb = 0.0;
+        double pa = 0.0, xa = 0.0, pb = 0.0, xb = 0.0;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
-            const int kk = REVERSE ? (NW - 1 - k) : k;
-            const double sa = slot[kk], sb = slot[NW + kk];
-            if (REVERSE ? (kk > w) : (kk < w)) {
-                pa = ta + sa;
-                pb = tb + sb;
+            const double va = slot[k], vb = slot[NW + k];
+            if (k < w) {
+                pa = xa + va;
+                pb = xb + vb;
             }
-            ta += sa;
-            tb += sb;
+            xa += va;
+            xb += vb;
         }
         a = pa + ea;
         b = pb + eb;
-        inc_a = pa + ia;
-        inc_b = pb + ib;
-        total_a = ta;
-        total_b = tb;
+        total_a = xa;
+        total_b = xb;
     }
 }
 
@@ -476,7 +581,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         bool finite = true;  // masses (and the scaled totals) are finite numbers
         double inv_u = 1.0, inv_v = 1.0;
         bool u_live = false, v_live = false;  // mass above the safe_divide floor -> carries gradient
-        float xu[E], xv[E];                   // raw bins (the gradient kernel needs them again at the end)
+        f32x2 x2[E];  // my (u, v) bin pairs (the gradient kernel needs them again at the end)
         int saved_corank[NCH];                // (loaded early: the global-memory latency hides behind stage 2)
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
@@ -490,56 +595,56 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         if constexpr (FROM_BINS) {
             // Pass 1: my E (u, v) bin pairs -> values to accumulate (x, x^2, |z| or |z|^2) and their local
             // sums, in packed fp32.  The per-thread sums T are then scanned across the CTA in fp64.
+            const bool inside = in_u && in_v;
 #pragma unroll
             for (int c = 0; c < E; ++c) {  // (past the row: finite garbage inside the landing rows)
                 if constexpr (CPLX) {  // |z|^2 = re^2 + im^2 directly (no square root), or |z|
                     float re, im;
                     lds64(rawU + 8 * c, re, im);
                     const float s2 = __fmaf_rn(re, re, __fmul_rn(im, im));
-                    xu[c] = square ? s2 : sqrtf(s2);
                     lds64(rawV + 8 * c, re, im);
                     const float t2 = __fmaf_rn(re, re, __fmul_rn(im, im));
-                    xv[c] = square ? t2 : sqrtf(t2);
+                    x2[c] = pack2(square ? s2 : sqrtf(s2), square ? t2 : sqrtf(t2));
                 } else {
-                    xu[c] = lds32(rawU + 4 * c);
-                    xv[c] = lds32(rawV + 4 * c);
+                    x2[c] = lds32x2(rawU + 4 * c, rawV + 4 * c);
                 }
             }
-            if (!in_u) {
+            if (!inside) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) xu[c] = (e0 + c < n) ? xu[c] : 0.0f;
-            }
-            if (!in_v) {
-#pragma unroll
-                for (int c = 0; c < E; ++c) xv[c] = (e0 + c < m) ? xv[c] : 0.0f;
+                for (int c = 0; c < E; ++c) x2[c] = mask2(x2[c], e0 + c < n, e0 + c < m);
             }
             const bool sq = square && !CPLX;
-            // Weights used as given (module-level `wasserstein_1d`, FLAG_RAW): the CDF is a plain cumsum, which
-            // the reference accumulates in fp64 -- reproduced exactly, because with a handful of atoms the strict
-            // `qs > 1` mask decides over a whole atom on the last ulp of the CDF.  Normalised spectra (every
-            // `Wasserstein1D` call) take the packed fp32 route: a few ulp, at a third of the instructions.
+            // Weights used as given (module-level `wasserstein_1d`, kernel mode MODE_RAW): the CDF is a plain
+            // cumsum, which the reference accumulates in fp64 -- reproduced exactly, because with a handful of
+            // atoms the strict `qs > 1` mask decides over a whole atom on the last ulp of the CDF.  Normalised
+            // spectra (every `Wasserstein1D` call) take the packed fp32 route: a few ulp, at a third of the
+            // instructions.
             constexpr bool exact = (MODE == MODE_RAW);
-            double off_u, off_v, inc_u, inc_v, tot_u, tot_v;
+            double off_u, off_v, nxt_u = 0.0, nxt_v = 0.0, tot_u, tot_v;
             if constexpr (exact) {
                 off_u = off_v = 0.0;
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    off_u += static_cast<double>(sq ? xu[c] * xu[c] : xu[c]);
-                    off_v += static_cast<double>(sq ? xv[c] * xv[c] : xv[c]);
+                    float a_, b_;
+                    unpack2(x2[c], a_, b_);
+                    off_u += static_cast<double>(sq ? a_ * a_ : a_);
+                    off_v += static_cast<double>(sq ? b_ * b_ : b_);
                 }
+                cta_scan2d<TPF>(off_u, off_v, tot_u, tot_v, scratch, tid);
             } else {
                 f32x2 t2 = 0;
+                if (sq) {  // (uniform branch: a per-element select costs three extra instructions)
 #pragma unroll
-                for (int c = 0; c < E; ++c) {
-                    const f32x2 x2 = pack2(xu[c], xv[c]);
-                    t2 = sq ? fma2(x2, x2, t2) : add2(t2, x2);  // (the same instruction as in pass 2: T is its last prefix)
+                    for (int c = 0; c < E; ++c) t2 = fma2(x2[c], x2[c], t2);  // (the same instruction as in pass 2:
+                } else {                                                      //  T is its last prefix)
+#pragma unroll
+                    for (int c = 0; c < E; ++c) t2 = add2(t2, x2[c]);
                 }
                 float Tu, Tv;
                 unpack2(t2, Tu, Tv);
-                off_u = static_cast<double>(Tu);
-                off_v = static_cast<double>(Tv);
+                // (the barrier inside also orders the raw reads before the CDF writes)
+                cta_scan2<TPF, false, true>(Tu, Tv, off_u, off_v, nxt_u, nxt_v, tot_u, tot_v, scratch, tid);
             }
-            cta_scan2<TPF, false>(off_u, off_v, inc_u, inc_v, tot_u, tot_v, scratch, tid);  // (its barrier also orders raw reads before CDF writes)
             const float mass_u = static_cast<float>(tot_u), mass_v = static_cast<float>(tot_v);
             u_live = mass_u > SAFE_EPS;  // utils.py:137: den <= eps -> eps
             v_live = mass_v > SAFE_EPS;
@@ -550,50 +655,61 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 u_live = v_live = false;
             }
             if constexpr (NW == 1) __syncwarp();
-            // Pass 2: CDF entry = base + (local prefix) * 1/mass with base = (sum of the threads before
-            // me) * 1/mass from the fp64 scan, split into an fp32 head and tail so that the one rounding that
-            // matters is the final add.  The local prefix is the SAME fp32 sequence as in pass 1, so the entry
-            // after my last bin is exactly the next thread's base; each entry is capped by that value, which
-            // keeps the row non-decreasing across thread boundaries whatever the roundings of the scaling do.
             if constexpr (exact) {
                 double tu = off_u, tv = off_v;
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
-                    tu += static_cast<double>(sq ? xu[c] * xu[c] : xu[c]);
-                    tv += static_cast<double>(sq ? xv[c] * xv[c] : xv[c]);
-                    if (in_u || e0 + c < n) sts32(A0 + 4 * (e0 + c), static_cast<float>(tu * inv_u));
-                    if (in_v || e0 + c < m) sts32(B0 + 4 * (e0 + c), static_cast<float>(tv * inv_v));
+                    float a_, b_;
+                    unpack2(x2[c], a_, b_);
+                    tu += static_cast<double>(sq ? a_ * a_ : a_);
+                    tv += static_cast<double>(sq ? b_ * b_ : b_);
+                    if (in_u || e0 + c < n) sts32(A0 + 4 * (e0 + c), static_cast<float>(tu));
+                    if (in_v || e0 + c < m) sts32(B0 + 4 * (e0 + c), static_cast<float>(tv));
                 }
             } else {
-            const double base_u = off_u * inv_u, base_v = off_v * inv_v;
-            const float bh_u = static_cast<float>(base_u), bh_v = static_cast<float>(base_v);
-            const float bl_u = static_cast<float>(base_u - static_cast<double>(bh_u));
-            const float bl_v = static_cast<float>(base_v - static_cast<double>(bh_v));
-            const float cap_u = static_cast<float>(inc_u * inv_u), cap_v = static_cast<float>(inc_v * inv_v);
-            const f32x2 bh2 = pack2(bh_u, bh_v), bl2 = pack2(bl_u, bl_v);
-            const f32x2 inv2 = pack2(static_cast<float>(inv_u), static_cast<float>(inv_v));
-            f32x2 p2 = 0;
+                // Pass 2: CDF entry = base + (local prefix) * 1/mass with base = (sum of the threads before
+                // me) * 1/mass from the fp64 scan, split into an fp32 head and tail so that the one rounding
+                // that matters is the final add.  The local prefix is the SAME fp32 sequence as in pass 1, so
+                // the entry after my last bin is the next thread's base; each entry is capped by that value
+                // (bitwise the next thread's head), which keeps the row non-decreasing across thread
+                // boundaries whatever the roundings of the scaling do.
+                const double base_u = off_u * inv_u, base_v = off_v * inv_v;
+                const float bh_u = static_cast<float>(base_u), bh_v = static_cast<float>(base_v);
+                const float bl_u = static_cast<float>(base_u - static_cast<double>(bh_u));
+                const float bl_v = static_cast<float>(base_v - static_cast<double>(bh_v));
+                const float cap_u = static_cast<float>(nxt_u * inv_u), cap_v = static_cast<float>(nxt_v * inv_v);
+                const f32x2 bh2 = pack2(bh_u, bh_v), bl2 = pack2(bl_u, bl_v);
+                const f32x2 inv2 = pack2(static_cast<float>(inv_u), static_cast<float>(inv_v));
+                auto emit = [&](auto SQ, auto INSIDE) {
+                    f32x2 p2 = 0;
 #pragma unroll
-            for (int c = 0; c < E; ++c) {
-                const f32x2 x2 = pack2(xu[c], xv[c]);
-                p2 = sq ? fma2(x2, x2, p2) : add2(p2, x2);
-                float ca, cb;
-                unpack2(add2(fma2(p2, inv2, bl2), bh2), ca, cb);
-                ca = fminf(ca, cap_u);
-                cb = fminf(cb, cap_v);
-                if (in_u || e0 + c < n) sts32(A0 + 4 * (e0 + c), ca);
-                if (in_v || e0 + c < m) sts32(B0 + 4 * (e0 + c), cb);
-            }
+                    for (int c = 0; c < E; ++c) {
+                        p2 = decltype(SQ)::value ? fma2(x2[c], x2[c], p2) : add2(p2, x2[c]);
+                        float ca, cb;
+                        unpack2(add2(fma2(p2, inv2, bl2), bh2), ca, cb);
+                        if (decltype(INSIDE)::value || e0 + c < n) sts32(A0 + 4 * (e0 + c), fminf(ca, cap_u));
+                        if (decltype(INSIDE)::value || e0 + c < m) sts32(B0 + 4 * (e0 + c), fminf(cb, cap_v));
+                    }
+                };
+                using T_ = std::true_type;
+                using F_ = std::false_type;
+                if (sq) {  // (uniform branches)
+                    if (inside) emit(T_{}, T_{}); else emit(T_{}, F_{});
+                } else {
+                    if (inside) emit(F_{}, T_{}); else emit(F_{}, F_{});
+                }
             }
             // NaN / inf anywhere (or an overflowing cut-mode scale) poisons the frame: the walk is skipped
             // (its +inf sentinels must stay unique) and NaN is written instead
             finite = (fabs(tot_u * inv_u) <= static_cast<double>(FLT_BIG)) &&
                      (fabs(tot_v * inv_v) <= static_cast<double>(FLT_BIG));
         } else {
+            float xu[E], xv[E];
 #pragma unroll
             for (int c = 0; c < E; ++c) {
                 xu[c] = (e0 + c < n) ? lds32(rawU + 4 * c) : 0.0f;
                 xv[c] = (e0 + c < m) ? lds32(rawV + 4 * c) : 0.0f;
+                x2[c] = 0;
             }
             cta_sync<TPF>();  // the rows are shifted in place by `lead`: all reads before any write
 #pragma unroll
@@ -917,29 +1033,32 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 // (packed fp32 on (u, v) pairs, like the CDF stage)
                 f32x2 ls2[E];
                 f32x2 s2 = 0, d2 = 0;
+                const bool inside = in_u && in_v;
+                if (inside) {
 #pragma unroll
-                for (int c = E - 1; c >= 0; --c) {
-                    float gu = 0.0f, gv = 0.0f, cu = 0.0f, cv = 0.0f;
-                    if (in_u || e0 + c < n) {
-                        gu = lds32(GA0 + 4 * (e0 + c));
-                        cu = lds32(A0 + 4 * (e0 + c));
+                    for (int c = E - 1; c >= 0; --c) {
+                        const f32x2 g2 = lds32x2(GA0 + 4 * (e0 + c), GB0 + 4 * (e0 + c));
+                        s2 = add2(s2, g2);
+                        d2 = fma2(g2, lds32x2(A0 + 4 * (e0 + c), B0 + 4 * (e0 + c)), d2);
+                        ls2[c] = s2;
                     }
-                    if (in_v || e0 + c < m) {
-                        gv = lds32(GB0 + 4 * (e0 + c));
-                        cv = lds32(B0 + 4 * (e0 + c));
+                } else {  // (reads past a row stay inside shared memory; the garbage is masked)
+#pragma unroll
+                    for (int c = E - 1; c >= 0; --c) {
+                        const f32x2 g2 = mask2(lds32x2(GA0 + 4 * (e0 + c), GB0 + 4 * (e0 + c)), e0 + c < n, e0 + c < m);
+                        const f32x2 c2 = mask2(lds32x2(A0 + 4 * (e0 + c), B0 + 4 * (e0 + c)), e0 + c < n, e0 + c < m);
+                        s2 = add2(s2, g2);
+                        d2 = fma2(g2, c2, d2);
+                        ls2[c] = s2;
                     }
-                    const f32x2 g2 = pack2(gu, gv);
-                    s2 = add2(s2, g2);
-                    d2 = fma2(g2, pack2(cu, cv), d2);
-                    ls2[c] = s2;
                 }
                 float su, sv, du, dv;
                 unpack2(s2, su, sv);
                 unpack2(d2, du, dv);
-                double off_u = static_cast<double>(su), off_v = static_cast<double>(sv), iu_, iv_, tu, tv;
-                cta_scan2<TPF, true>(off_u, off_v, iu_, iv_, tu, tv, scratch + 4 * NW, tid);
-                (void)iu_;
-                (void)iv_;
+                double off_u, off_v, nu_ = 0.0, nv_ = 0.0, tu, tv;
+                cta_scan2<TPF, true, false>(su, sv, off_u, off_v, nu_, nv_, tu, tv, scratch + 4 * NW, tid);
+                (void)nu_;
+                (void)nv_;
                 double dot_u = static_cast<double>(du), dot_v = static_cast<double>(dv);
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -981,11 +1100,11 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
 #pragma unroll
                     for (int c = 0; c < E; ++c) {
                         f32x2 g2 = mul2(add2(b2, ls2[c]), k2);
-                        if (square) g2 = mul2(g2, pack2(xu[c], xv[c]));
+                        if (square) g2 = mul2(g2, x2[c]);
                         float ga, gb;
                         unpack2(g2, ga, gb);
-                        if (in_u || e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), ga);
-                        if (in_v || e0 + c < m) sts32(GB0 + lead_v + 4 * (e0 + c), gb);
+                        if (inside || e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), ga);
+                        if (inside || e0 + c < m) sts32(GB0 + lead_v + 4 * (e0 + c), gb);
                     }
                 } else {
                     // d|z|^2/dz = 2z, d|z|/dz = z/|z| (0 at 0, like torch.abs): dL/dz = f * z, written over z.
