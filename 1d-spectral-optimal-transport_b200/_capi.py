@@ -58,7 +58,12 @@ SIGNATURES = {
     "sot_max_bins": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32]),
     "sot_set_tuning": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "sot_launch_count": (ctypes.c_int64, []),
+    "sot_mss_forward_device": (ctypes.c_int, [_V, _V, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int32,
+                                              ctypes.c_float, _V, _V]),
+    "sot_mss_backward_device": (ctypes.c_int, [_V, _V, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int32,
+                                               ctypes.c_float, _V, _V, _V, _V]),
 }
+SOT_MSS_L1, SOT_MSS_L2 = 0, 1
 
 _lib = None
 _lock = threading.Lock()
@@ -69,7 +74,8 @@ class SotError(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; SOT_B200_LIBRARY points developers' tuning experiments at another build of it."""
+    return os.environ.get("SOT_B200_LIBRARY") or _build.LIB_PATH
 
 
 def load(build_if_needed: bool = True):
@@ -78,12 +84,13 @@ def load(build_if_needed: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        if build_if_needed and _build.is_stale():
+        path = library_path()
+        if path == _build.LIB_PATH and build_if_needed and _build.is_stale():
             _build.build()
-        if not os.path.exists(_build.LIB_PATH):
-            raise SotError(f"{_build.LIB_PATH} is missing: build it with `python -m sot_b200.build` "
+        if not os.path.exists(path):
+            raise SotError(f"{path} is missing: build it with `python -m sot_b200.build` "
                            "(this package has no CPU or eager fallback)")
-        lib = ctypes.CDLL(_build.LIB_PATH)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError here = header / library mismatch
             fn.restype, fn.argtypes = res, args
@@ -302,3 +309,42 @@ def launch_count() -> int:
 
 def max_bins(with_grad: bool = True, shared_positions: bool = True) -> int:
     return int(load().sot_max_bins(int(with_grad), int(shared_positions)))
+
+
+def _mss_check(zt, zv):
+    for t, name in ((zt, "target spectrogram"), (zv, "spectrogram")):
+        if not t.is_cuda:
+            raise SotError(f"sot_b200: the {name} lives on {t.device}; the kernels are CUDA only "
+                           "(no CPU fallback exists by design)")
+        if t.dtype != torch.complex64:
+            raise TypeError(f"sot_b200: the {name} must be complex64, got {t.dtype}")
+    if zt.shape != zv.shape or zt.device != zv.device:
+        raise ValueError(f"sot_b200: spectrogram shapes differ: {tuple(zt.shape)} vs {tuple(zv.shape)}")
+    if zt.stride() != zv.stride():
+        raise ValueError("sot_b200: the two spectrograms must have the same (dense) memory layout")
+
+
+def mss_forward(zt, zv, mag_weight, logmag_weight, loss_type, post_scale, total=None):
+    """total (1,) float64 += post_scale * sum_i [mag_w d(|zt|,|zv|) + logmag_w d(safe_log|zt|, safe_log|zv|)]."""
+    lib = load()
+    _mss_check(zt, zv)
+    if total is None:
+        total = torch.zeros(1, dtype=torch.float64, device=zt.device)
+    with torch.cuda.device(zt.device):
+        _check(lib.sot_mss_forward_device(_ptr(zt), _ptr(zv), zt.numel(), float(mag_weight), float(logmag_weight),
+                                          int(loss_type), float(post_scale), _ptr(total), _stream(zt.device)))
+    return total
+
+
+def mss_backward(zt, zv, mag_weight, logmag_weight, loss_type, post_scale, scale, want_t=True, want_v=True):
+    """Complex gradients of scale * post_scale * S w.r.t. zt / zv (same layout as the inputs)."""
+    lib = load()
+    _mss_check(zt, zv)
+    _dev_tensor(scale, "scale")
+    gt = torch.empty_like(zt) if want_t else None
+    gv = torch.empty_like(zv) if want_v else None
+    with torch.cuda.device(zt.device):
+        _check(lib.sot_mss_backward_device(_ptr(zt), _ptr(zv), zt.numel(), float(mag_weight), float(logmag_weight),
+                                           int(loss_type), float(post_scale), _ptr(scale), _ptr(gt), _ptr(gv),
+                                           _stream(zt.device)))
+    return gt, gv

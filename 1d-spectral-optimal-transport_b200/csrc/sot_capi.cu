@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -185,6 +186,9 @@ extern "C" {
 int sot_abi_version(void) { return SOT_B200_ABI_VERSION; }
 const char* sot_last_error(void) { return g_error; }
 int64_t sot_launch_count(void) { return g_launches.load(); }
+// shared with sot_mss.cu (not part of the public header)
+int sot_mss_launch_count_add(void) { return static_cast<int>(g_launches.fetch_add(1, std::memory_order_relaxed)); }
+int sot_mss_fail(int code, const char* msg) { return code < 0 ? fail(code, "%s", msg) : (snprintf(g_error, sizeof(g_error), "%s", msg), code); }
 
 int sot_set_tuning(int32_t tpf, int32_t e, int32_t chains) {
     if (tpf == 0 && e == 0) {
@@ -422,7 +426,12 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
     if (N == 0) return SOT_OK;
     const int n = hp->n_u, m = hp->n_v;
     const bool want_grad = grad_u != nullptr || grad_v != nullptr;
-    long long chunk = (32LL << 20) / (4LL * (n + m));  // ~32 MiB of input per chunk
+    long long chunk_bytes = 32LL << 20;  // ~32 MiB of input per chunk; SOT_HOST_CHUNK_MIB overrides (tuning)
+    if (const char* env = getenv("SOT_HOST_CHUNK_MIB")) {
+        const long long mib = atoll(env);
+        if (mib >= 1 && mib <= 4096) chunk_bytes = mib << 20;
+    }
+    long long chunk = chunk_bytes / (4LL * (n + m));
     chunk = (chunk / 4) * 4;
     if (chunk < 4) chunk = 4;
     if (chunk > N) chunk = ((N + 3) / 4) * 4;

@@ -420,7 +420,14 @@ SOT_DEVINL void cta_scan2d(double& a, double& b, double& total_a, double& total_
 // within a sane register budget (forward >= 40, gradient >= 64 registers per thread).
 constexpr int min_ctas(int tpf, int e, int smem_bytes, int out) {
     const int by_smem = (227 * 1024) / (smem_bytes + 1024);
-    const int regs = out == OUT_GRAD ? (e <= 9 ? 64 : (e <= 17 ? 96 : 168)) : (e <= 9 ? 40 : (e <= 17 ? 64 : 128));
+#ifndef SOT_REGS_GRAD_E17  // (tuning experiments: -DSOT_REGS_GRAD_E17=.. -DSOT_REGS_LOSS_E17=..)
+#define SOT_REGS_GRAD_E17 96
+#endif
+#ifndef SOT_REGS_LOSS_E17
+#define SOT_REGS_LOSS_E17 64
+#endif
+    const int regs = out == OUT_GRAD ? (e <= 9 ? 64 : (e <= 17 ? SOT_REGS_GRAD_E17 : 168))
+                                     : (e <= 9 ? 40 : (e <= 17 ? SOT_REGS_LOSS_E17 : 128));
     const int by_regs = 65536 / (tpf * regs);
     const int c = by_smem < by_regs ? by_smem : by_regs;
     return c < 1 ? 1 : (c > 32 ? 32 : c);

@@ -119,19 +119,30 @@ def _support(pos: torch.Tensor, like: torch.Tensor, name: str) -> torch.Tensor:
     return pos.contiguous()
 
 
+def _version(t: torch.Tensor):
+    """Version counter of a caller tensor, or None for an inference tensor (`torch.inference_mode`, which
+    `metrics.wasserstein_distance` runs under, metrics.py:144): those are never cached."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
+
+
 def _is_ascending(pos: torch.Tensor, owner: torch.Tensor) -> bool:
     """One device->host read per distinct (tensor object, version) of the caller's positions
     tensor `owner`; cached after that (a `fixed_x` buffer or a grid the caller keeps is checked once)."""
     key = id(owner)
+    version = _version(owner)
     hit = _sorted_cache.get(key)
-    if hit is not None and hit[0]() is owner and hit[1] == owner._version:
+    if hit is not None and version is not None and hit[0]() is owner and hit[1] == version:
         return hit[2]
     ok = bool((pos[..., 1:] >= pos[..., :-1]).all().item()) if pos.shape[-1] > 1 else True
-    try:
-        ref = weakref.ref(owner, lambda _, k=key: _sorted_cache.pop(k, None))
-        _sorted_cache[key] = (ref, owner._version, ok)
-    except TypeError:
-        pass
+    if version is not None:
+        try:
+            ref = weakref.ref(owner, lambda _, k=key: _sorted_cache.pop(k, None))
+            _sorted_cache[key] = (ref, version, ok)
+        except TypeError:
+            pass
     return ok
 
 
@@ -160,9 +171,11 @@ def _uniform_grid(pu: torch.Tensor, pv: torch.Tensor, owner_u: torch.Tensor, own
     if pu.ndim != 1 or pv.ndim != 1 or pu.shape[0] < 2 or pv.shape[0] < 2:
         return False
     key = (id(owner_u), id(owner_v))
+    ver_u, ver_v = _version(owner_u), _version(owner_v)
+    cacheable = ver_u is not None and ver_v is not None
     hit = _uniform_cache.get(key)
-    if (hit is not None and hit[0]() is owner_u and hit[1]() is owner_v and hit[2] == owner_u._version
-            and hit[3] == owner_v._version):
+    if (hit is not None and cacheable and hit[0]() is owner_u and hit[1]() is owner_v and hit[2] == ver_u
+            and hit[3] == ver_v):
         return hit[4]
     h = pu[1] - pu[0]
     ok = (pu == pu[0] + torch.arange(pu.shape[0], device=pu.device) * h).all() & \
@@ -175,12 +188,12 @@ def _uniform_grid(pu: torch.Tensor, pv: torch.Tensor, owner_u: torch.Tensor, own
         span = max(pu.shape[0], pv.shape[0]) + abs(u0 / h_val) + abs(v0 / h_val)
         uniform = (mant == 0.5 and float(u0 / h_val).is_integer() and float(v0 / h_val).is_integer()
                    and span < 2 ** 23)
-    try:
-        drop = lambda _, k=key: _uniform_cache.pop(k, None)  # noqa: E731
-        _uniform_cache[key] = (weakref.ref(owner_u, drop), weakref.ref(owner_v, drop), owner_u._version,
-                               owner_v._version, uniform)
-    except TypeError:
-        pass
+    if cacheable:
+        try:
+            drop = lambda _, k=key: _uniform_cache.pop(k, None)  # noqa: E731
+            _uniform_cache[key] = (weakref.ref(owner_u, drop), weakref.ref(owner_v, drop), ver_u, ver_v, uniform)
+        except TypeError:
+            pass
     return uniform
 
 

@@ -143,6 +143,23 @@ int sot_abi_version(void);
 const char* sot_last_error(void);
 /* Largest row length (max(n_u, n_v)) the kernels accept for the given outputs. */
 int sot_max_bins(int32_t with_grad, int32_t shared_positions);
+/* ---- Multi-scale spectral loss term (row f3; losses.py:365-425 `MSSLoss`, :7-36 `mean_difference`,
+ * utils.py:145-151 `safe_log`) for ONE fft size, straight from the two complex64 spectrograms zt (target) and zv
+ * (prediction) of `count` elements each, any layout:
+ *     S = sum_i mag_weight * d(|zt_i|, |zv_i|) + logmag_weight * d(safe_log|zt_i|, safe_log|zv_i|),
+ *     d(a, b) = |a - b| (SOT_MSS_L1) or (a - b)^2 (SOT_MSS_L2).
+ * forward:  *sum_out += post_scale * S   (fp64, device memory; the caller zeroes it; post_scale = 1/count gives the
+ *           reference's mean, and one accumulator can collect all fft sizes).
+ * backward: grad_z* = (*scale) * post_scale * dS/dz* as complex64 (dL/dre, dL/dim); `scale` is a device scalar
+ *           (NULL = 1); either gradient may be NULL. */
+#define SOT_MSS_L1 0
+#define SOT_MSS_L2 1
+int sot_mss_forward_device(const float* zt, const float* zv, int64_t count, float mag_weight, float logmag_weight,
+                           int32_t loss_type, float post_scale, double* sum_out, void* stream);
+int sot_mss_backward_device(const float* zt, const float* zv, int64_t count, float mag_weight, float logmag_weight,
+                            int32_t loss_type, float post_scale, const float* scale, float* grad_zt, float* grad_zv,
+                            void* stream);
+
 /* Tuning override for benchmarking: threads per frame (32/64/128/256), bins per thread (odd) and
  * merge chains per thread (1/2, 0 = any); 0, 0, 0 restores the built-in choice.  Returns SOT_EINVAL
  * if that combination is not compiled in. */
