@@ -111,9 +111,10 @@ struct Layout {
     static constexpr uint32_t POS_OFF = 2 * ROW;  // cdf address -> position address (two rows; none when UNI)
     static constexpr uint32_t PROWS = UNI ? 0 : 2;
     static constexpr uint32_t G_OFF = (2 + PROWS) * ROW;  // cdf address -> dL/dCDF address (two rows; also output staging)
-    // (A separate landing zone for the raw rows, so that the next frame is fetched while this one is
-    // still being walked, was measured: the mbarrier wait disappears from the stall samples, the run
-    // time does not change -- the kernel is bound by issue slots and shared-memory wavefronts.)
+    // (A separate landing zone for the raw rows, so that the next frame is fetched a whole frame ahead, was
+    // measured twice -- on the shared-memory-bound v3 kernel and again on the packed-fp32 one: the mbarrier
+    // wait disappears from the stall samples, the run time does not change (other resident CTAs fill the
+    // wait) -- so the rows stay in place and the shared memory goes to resident CTAs.)
     // Complex (STFT) input: the raw rows are twice as wide, land in their own two double rows and, in the
     // gradient kernel, are overwritten in place by the complex gradient rows (= output staging).
     static constexpr uint32_t REAL_ROWS = 2 + PROWS + ((OUT == OUT_GRAD) ? 2 : 0);
