@@ -98,3 +98,18 @@ def test_metrics_wasserstein_distance(p):
     g = G.load(f"metric_wd_p{p}")
     value = metrics.wasserstein_distance(g["audio_x"].to(DEV), g["audio_y"].to(DEV), p=p, n_fft=512)
     assert abs(value.item() - g["value"].item()) <= 1e-5 * abs(g["value"].item())
+
+
+def test_training_step_example_reduces_the_loss():
+    """examples/train_step.py (reduced): the paper's loss mix inside a plain training loop."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "train_step.py"), "--steps", "60", "--signals", "32",
+                          "--lr", "1e-3"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["last_loss"] < line["first_loss"] and line["frames_per_s"] > 0
