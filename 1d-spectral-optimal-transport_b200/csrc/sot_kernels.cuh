@@ -1105,14 +1105,24 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 const float kv = finite ? static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f) : f_nan();
                 if constexpr (!CPLX) {
                     const f32x2 b2 = pack2(bu, bv), k2 = pack2(ku, kv);
+                    const uint32_t out_u = GA0 + lead_u + 4 * e0, out_v = GB0 + lead_v + 4 * e0;
+                    auto emit = [&](auto SQ, auto INSIDE) {  // (uniform choices hoisted out of the element loop)
 #pragma unroll
-                    for (int c = 0; c < E; ++c) {
-                        f32x2 g2 = mul2(add2(b2, ls2[c]), k2);
-                        if (square) g2 = mul2(g2, x2[c]);
-                        float ga, gb;
-                        unpack2(g2, ga, gb);
-                        if (inside || e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), ga);
-                        if (inside || e0 + c < m) sts32(GB0 + lead_v + 4 * (e0 + c), gb);
+                        for (int c = 0; c < E; ++c) {
+                            f32x2 g2 = mul2(add2(b2, ls2[c]), k2);
+                            if constexpr (decltype(SQ)::value) g2 = mul2(g2, x2[c]);
+                            float ga, gb;
+                            unpack2(g2, ga, gb);
+                            if (decltype(INSIDE)::value || e0 + c < n) sts32(out_u + 4 * c, ga);
+                            if (decltype(INSIDE)::value || e0 + c < m) sts32(out_v + 4 * c, gb);
+                        }
+                    };
+                    using T_ = std::true_type;
+                    using F_ = std::false_type;
+                    if (square) {
+                        if (inside) emit(T_{}, T_{}); else emit(T_{}, F_{});
+                    } else {
+                        if (inside) emit(F_{}, T_{}); else emit(F_{}, F_{});
                     }
                 } else {
                     // d|z|^2/dz = 2z, d|z|/dz = z/|z| (0 at 0, like torch.abs): dL/dz = f * z, written over z.
