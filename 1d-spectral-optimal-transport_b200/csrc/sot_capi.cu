@@ -169,8 +169,8 @@ int launch(const sot_problem* p, sot::LaunchRequest& r, void* stream) {
     if (c == nullptr)
         return fail(SOT_ETOOBIG, "rows of %d / %d bins exceed the largest kernel configuration (%d bins)", p->n_u,
                     p->n_v, sot_max_bins(1, 1));
-    // complex input keeps two double-width landing rows on top of the real rows: up to 10 rows of 4*rs bytes
-    if ((p->flags & SOT_COMPLEX_INPUT) && 40 * c->rs + 1024 > 227 * 1024)
+    // complex input keeps two double-width landing rows on top of the real rows: up to 10 rows of 4*rs bytes (+ pad, head)
+    if ((p->flags & SOT_COMPLEX_INPUT) && 41 * c->rs + 8192 > 227 * 1024)
         return fail(SOT_ETOOBIG, "complex rows of %d / %d bins do not fit in shared memory (limit %d bins)", p->n_u,
                     p->n_v, 4352);
     cudaError_t e = c->fn(r, static_cast<cudaStream_t>(stream));

@@ -107,7 +107,14 @@ SOT_DEVINL float f_nan() { return __int_as_float(0x7fc00000); }
 template <int TPF, int RS, int OUT, int NCH, bool UNI, bool CPLX>
 struct Layout {
     static constexpr uint32_t ROW = 4u * RS;
-    static constexpr uint32_t A = 0, B = ROW;     // CDF rows (also the landing zone of the raw rows)
+    // small per-CTA structures first, the rows after them: a thread whose bins lie past the end of a row reads
+    // (and masks) whatever follows -- after the last row that is the PAD below, never live scratch data
+    static constexpr uint32_t SCRATCH = 0;                        // 8 doubles per warp
+    static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per chunk + end marker
+    static constexpr uint32_t CARRY = MBOX + 8u * (NCH * TPF + 1);
+    static constexpr uint32_t MBAR = (CARRY + 4u * NCH * TPF + 15u) & ~15u;
+    static constexpr uint32_t HEAD = (MBAR + 16u + 127u) & ~127u;
+    static constexpr uint32_t A = HEAD, B = HEAD + ROW;  // CDF rows (also the landing zone of the raw rows)
     static constexpr uint32_t POS_OFF = 2 * ROW;  // cdf address -> position address (two rows; none when UNI)
     static constexpr uint32_t PROWS = UNI ? 0 : 2;
     static constexpr uint32_t G_OFF = (2 + PROWS) * ROW;  // cdf address -> dL/dCDF address (two rows; also output staging)
@@ -118,14 +125,11 @@ struct Layout {
     // Complex (STFT) input: the raw rows are twice as wide, land in their own two double rows and, in the
     // gradient kernel, are overwritten in place by the complex gradient rows (= output staging).
     static constexpr uint32_t REAL_ROWS = 2 + PROWS + ((OUT == OUT_GRAD) ? 2 : 0);
-    static constexpr uint32_t LAND = CPLX ? REAL_ROWS * ROW : A;
+    static constexpr uint32_t LAND = CPLX ? HEAD + REAL_ROWS * ROW : A;
     static constexpr uint32_t LAND_ROW = CPLX ? 2 * ROW : ROW;  // bytes between the u and the v landing row
     static constexpr uint32_t ROWS = REAL_ROWS + (CPLX ? 4 : 0);
-    static constexpr uint32_t SCRATCH = ROWS * ROW;               // 8 doubles per warp
-    static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per chunk + end marker
-    static constexpr uint32_t CARRY = MBOX + 8u * (NCH * TPF + 1);
-    static constexpr uint32_t MBAR = (CARRY + 4u * NCH * TPF + 15u) & ~15u;
-    static constexpr uint32_t TOTAL = MBAR + 16u;
+    static constexpr uint32_t PAD = ROW / 4 + 64u;  // over-read room after the last row (TPF * E bins >= a row)
+    static constexpr uint32_t TOTAL = HEAD + ROWS * ROW + PAD;
     static constexpr int MAX_BINS = RS - 7;  // sentinel + up to 3 floats of lead + rounding of the bulk window
 };
 
@@ -521,8 +525,8 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         pv0 = args.pos_v[0];
         hstep = args.pos_u[1] - pu0;
     } else if (pos_shared) {  // positions once per CTA
-        for (int idx = tid; idx <= n; idx += TPF) fsm[2 * RS + idx] = args.pos_u[min(idx, n - 1)];
-        for (int idx = tid; idx <= m; idx += TPF) fsm[3 * RS + idx] = args.pos_v[min(idx, m - 1)];
+        for (int idx = tid; idx <= n; idx += TPF) fsm[(LY::A + LY::POS_OFF) / 4 + idx] = args.pos_u[min(idx, n - 1)];
+        for (int idx = tid; idx <= m; idx += TPF) fsm[(LY::B + LY::POS_OFF) / 4 + idx] = args.pos_v[min(idx, m - 1)];
     }
     (void)pu0;
     (void)pv0;
@@ -581,8 +585,8 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         if (!UNI && !pos_shared) {  // per-frame supports
             const float* gpu = args.pos_u + frame * args.pos_u_stride;
             const float* gpv = args.pos_v + frame * args.pos_v_stride;
-            for (int idx = tid; idx <= n; idx += TPF) fsm[2 * RS + idx] = gpu[min(idx, n - 1)];
-            for (int idx = tid; idx <= m; idx += TPF) fsm[3 * RS + idx] = gpv[min(idx, m - 1)];
+            for (int idx = tid; idx <= n; idx += TPF) fsm[(LY::A + LY::POS_OFF) / 4 + idx] = gpu[min(idx, n - 1)];
+            for (int idx = tid; idx <= m; idx += TPF) fsm[(LY::B + LY::POS_OFF) / 4 + idx] = gpv[min(idx, m - 1)];
         }
 
         float acc[NCH] = {};  // my part of the frame's loss
