@@ -156,6 +156,8 @@ sot::FrameArgs base_args(const sot_problem* p) {
     a.m = p->n_v;
     a.p = p->p;
     a.flags = p->flags;
+    a.one = a.one_b = 1.0f;
+    a.neg_zero = a.neg_zero_b = -0.0f;
     return a;
 }
 

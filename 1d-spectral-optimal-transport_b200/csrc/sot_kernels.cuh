@@ -98,6 +98,10 @@ struct FrameArgs {
     int n, m;
     float p;
     int flags;
+    // 1.0f and -0.0f as RUN-TIME values (set by the launcher): x * one + neg_zero == x exactly, and because
+    // ptxas cannot fold it, a predicated FFMA (fma pipe, two warp-instructions per clock pair) can stand in
+    // for an FSEL (alu pipe, half that rate) in the merge walk, which is bound by the alu pipe
+    float one, neg_zero, one_b, neg_zero_b;  // (two copies: identical expressions would be merged and re-selected)
 };
 
 SOT_DEVINL float f_inf() { return __int_as_float(0x7f800000); }
@@ -204,9 +208,15 @@ SOT_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 // array from the SELECTED address: a pair of predicated loads (one per side, half the lanes each)
 // costs a shared-memory wavefront per instruction, and wavefronts are what bounds this kernel.
 // `consumed` = address of the CDF entry that was taken.  POS4 = POS_OFF + 4.
+// The value selects are predicated FFMAs (x * one + neg_zero with run-time 1.0f / -0.0f, see FrameArgs): the
+// walk is bound by the alu pipe (FSEL / FSETP / FMNMX / integer adds, one warp-instruction per two clocks)
+// while the fma pipe has room; `k` = the four constants.
+struct WalkConsts {
+    float one, nz, one_b, nz_b;
+};
 template <uint32_t POS4>
 SOT_DEVINL void advance(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB,
-                        uint32_t& consumed) {
+                        uint32_t& consumed, const WalkConsts& k) {
     asm volatile(
         "{\n"
         ".reg .pred tv;\n"
@@ -217,42 +227,36 @@ SOT_DEVINL void advance(float& a, float& pa, float& b, float& pb, uint32_t& adrA
         "ld.shared.f32 np, [%6+%7];\n"
         "@tv  add.u32 %5, %5, 4;\n"
         "@!tv add.u32 %4, %4, 4;\n"
-        "selp.f32 %2, nv, %2, tv;\n"
-        "selp.f32 %3, np, %3, tv;\n"
-        "selp.f32 %0, %0, nv, tv;\n"
-        "selp.f32 %1, %1, np, tv;\n"
+        "@tv  fma.rn.f32 %2, nv, %8, %9;\n"
+        "@tv  fma.rn.f32 %3, np, %8, %9;\n"
+        "@!tv fma.rn.f32 %0, nv, %10, %11;\n"
+        "@!tv fma.rn.f32 %1, np, %10, %11;\n"
         "}"
         : "+f"(a), "+f"(pa), "+f"(b), "+f"(pb), "+r"(adrA), "+r"(adrB), "=&r"(consumed)
-        : "n"(POS4));
+        : "n"(POS4), "f"(k.one), "f"(k.nz), "f"(k.one_b), "f"(k.nz_b));
 }
 // Uniform-grid advance: no position load; `d` = pos_u[head] - pos_v[head] moves by exactly +h when u
 // advances and -h when v advances -- except onto the +inf sentinel, whose position repeats the last
 // one (the reference's index clamp).
 SOT_DEVINL void advance_uni(float& a, float& d, float& b, uint32_t& adrA, uint32_t& adrB, uint32_t& consumed,
-                            float h, float neg_h) {
+                            float h, float neg_h, const WalkConsts& k) {
     asm volatile(
         "{\n"
-        ".reg .pred tv, live;\n"
-        ".reg .f32 nv, dh;\n"
+        ".reg .pred tv;\n"
+        ".reg .f32 nv, dh, live;\n"
         "setp.lt.f32 tv, %2, %0;\n"
         "selp.u32 %5, %4, %3, tv;\n"
         "ld.shared.f32 nv, [%5+4];\n"
         "@tv  add.u32 %4, %4, 4;\n"
         "@!tv add.u32 %3, %3, 4;\n"
         "selp.f32 dh, %7, %6, tv;\n"
-        "setp.lt.f32 live, nv, 0f7F800000;\n"
-        "selp.f32 %2, nv, %2, tv;\n"
-        "selp.f32 %0, %0, nv, tv;\n"
-        "@live add.rn.f32 %1, %1, dh;\n"
+        "sub.rn.sat.f32 live, 0f7F7FFFFF, nv;\n"  // 1 for a CDF entry, 0 for the +inf sentinel
+        "@tv  fma.rn.f32 %2, nv, %8, %9;\n"
+        "@!tv fma.rn.f32 %0, nv, %10, %11;\n"
+        "fma.rn.f32 %1, dh, live, %1;\n"
         "}"
         : "+f"(a), "+f"(d), "+f"(b), "+r"(adrA), "+r"(adrB), "=&r"(consumed)
-        : "f"(h), "f"(neg_h));
-}
-
-template <uint32_t POS4>
-SOT_DEVINL void advance_fwd(float& a, float& pa, float& b, float& pb, uint32_t& adrA, uint32_t& adrB) {
-    uint32_t consumed;
-    advance<POS4>(a, pa, b, pb, adrA, adrB, consumed);
+        : "f"(h), "f"(neg_h), "f"(k.one), "f"(k.nz), "f"(k.one_b), "f"(k.nz_b));
 }
 
 // fp64 reciprocal of a positive float >= 1e-7: hardware approximation + two Newton steps
@@ -489,6 +493,11 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     // contributions with q above `thr` are dropped: the strict `qs > 1` mask (losses.py:307) when
     // limiting, otherwise nothing a real slot can reach
     const float thr = (args.flags & FLAG_LIMIT) ? 1.0f : FLT_BIG;
+    // the same test on the fma pipe: keep(q) = sat((thr+ - q) * 2^60) is exactly 1 for q <= thr and 0 above
+    // (thr+ = the float after thr; without a limit the constant is +inf and keep == 1 for every finite q)
+    const float keep_c = (args.flags & FLAG_LIMIT) ? 1.00000011920928955078125f * 1152921504606846976.0f
+                                                   : __int_as_float(0x7f800000);
+    const WalkConsts wk{args.one, args.neg_zero, args.one_b, args.neg_zero_b};
     const uint32_t sb = smem_u32(smem);
     const uint32_t A0 = sb + LY::A, B0 = sb + LY::B;
 
@@ -812,16 +821,16 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     constexpr int ch = decltype(CH)::value;
                     const float q = fminf(a[ch], b[ch]);
                     const float D = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
-                    float dq = q - qprev[ch];
-                    dq = (q > thr) ? 0.0f : dq;
+                    float keep;
+                    asm("fma.rn.sat.f32 %0, %1, 0fDD800000, %2;" : "=f"(keep) : "f"(q), "f"(keep_c));  // q * -2^60 + c
+                    const float dq = __fmul_rn(q - qprev[ch], keep);
                     acc[ch] = fmaf(dq, D, acc[ch]);
                     qprev[ch] = q;
-                    if constexpr (UNI) {
-                        uint32_t consumed;
-                        advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed, hstep, -hstep);
-                    } else {
-                        advance_fwd<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch]);
-                    }
+                    uint32_t consumed;
+                    if constexpr (UNI)
+                        advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed, hstep, -hstep, wk);
+                    else
+                        advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed, wk);
                 };
                 int s = 0;
                 if constexpr (NCH == 2) {
@@ -873,29 +882,29 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 for (int ch = 0; ch < NCH; ++ch)
                     if (cnt[ch] > 0) {
                         if constexpr (UNI)
-                            advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed[ch], hstep, -hstep);
+                            advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed[ch], hstep, -hstep, wk);
                         else
-                            advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
+                            advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch], wk);
                     }
                 auto gstep = [&](auto CH) {
                     constexpr int ch = decltype(CH)::value;
                     const float q = fminf(a[ch], b[ch]);
                     const float D = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
-                    const bool over = q > thr;
-                    float dq = q - qprev[ch];
-                    dq = over ? 0.0f : dq;
-                    acc[ch] = fmaf(dq, D, acc[ch]);
+                    float keep;  // 1 for q <= thr, 0 above (fma pipe, see keep_c)
+                    asm("fma.rn.sat.f32 %0, %1, 0fDD800000, %2;" : "=f"(keep) : "f"(q), "f"(keep_c));
+                    const float fmd = __fmul_rn(D, keep);  // m * d of a group that starts here
+                    acc[ch] = fmaf(q - qprev[ch], fmd, acc[ch]);
                     const bool same = (q == qprev[ch]);
-                    const float md = same ? md_prev[ch] : (over ? 0.0f : D);
+                    const float md = same ? md_prev[ch] : fmd;
                     sts32o<LY::G_OFF>(consumed[ch], md_prev[ch] - md);  // dL/dCDF of the previous slot (0 inside a group)
                     fix[ch] = (inherited[ch] && !same) ? consumed[ch] : fix[ch];
                     inherited[ch] = inherited[ch] && same;
                     md_prev[ch] = md;
                     qprev[ch] = q;
                     if constexpr (UNI)
-                        advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed[ch], hstep, -hstep);
+                        advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed[ch], hstep, -hstep, wk);
                     else
-                        advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch]);
+                        advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed[ch], wk);
                 };
                 int s = 1;
                 if constexpr (NCH == 2) {
@@ -971,7 +980,8 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                         acc[ch] = fmaf(dq, transport_cost<PMODE>(pa[ch], pb[ch], args.p), acc[ch]);
                         qprev[ch] = q;
                         if (take_v) ++j; else ++i;
-                        advance_fwd<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch]);
+                        uint32_t consumed;
+                        advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed, wk);
                     }
                     sts32(carry + 4u * (NCH * tid + ch),
                           __int_as_float((cnt[ch] == 0 || inherited) ? -1 : ((is << 16) | js)));
