@@ -212,11 +212,18 @@ def main():
     if grid == "linear":  # what the module detects for these grids (exact i * 2**-k positions)
         flags |= _capi.SOT_UNIFORM_GRID
     up = torch.full((args.frames,), 1.0 / (args.frames * world), device=dev)
+    # the launch the timed step's backward makes: upstream scalar on the device, merge-path co-ranks saved by
+    # the forward launch (`fused` mode has no separate backward launch: time the plain fused entry point)
+    scale_dev = torch.full((1,), 1.0 / (args.frames * world), device=dev)
+    coranks = _capi.forward_sum(x, y, pos, pos_y, 2.0, flags, save_coranks=True)[2]
     k_ms = []
     for it in range(3 + args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        _capi.forward_backward(x, y, pos, pos_y, 2.0, flags, upstream=up, want_loss=False)
+        if loss_fn.backward_mode == "recompute":
+            _capi.forward_backward_scaled(x, y, pos, pos_y, 2.0, flags, scale_dev, coranks=coranks)
+        else:
+            _capi.forward_backward(x, y, pos, pos_y, 2.0, flags, upstream=up, want_loss=False)
         b.record()
         b.synchronize()
         if it >= 3:
@@ -225,7 +232,10 @@ def main():
     for it in range(3 + args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        _capi.forward(x, y, pos, pos_y, 2.0, flags)
+        if loss_fn.backward_mode == "recompute":  # the step's forward launch: sum on the device, co-ranks saved
+            _capi.forward_sum(x, y, pos, pos_y, 2.0, flags, save_coranks=True)
+        else:
+            _capi.forward(x, y, pos, pos_y, 2.0, flags)
         b.record()
         b.synchronize()
         if it >= 3:
@@ -234,7 +244,7 @@ def main():
     sampler.join()
     k_avg, f_avg = sum(k_ms) / len(k_ms), sum(f_ms) / len(f_ms)
     peak, peak_src = peaks()
-    bytes_bwd = (16 * F + 4) * args.frames  # reads u, v, upstream; writes grad_u, grad_v
+    bytes_bwd = (16 * F + 4) * args.frames  # reads u, v, upstream; writes grad_u, grad_v (co-ranks: 128 B, not counted)
     bytes_fwd = (8 * F + 4) * args.frames   # reads u, v; writes loss
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
