@@ -444,6 +444,12 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
 
     HostWorkspace& w = g_ws[device];
     int rc = SOT_OK;
+    constexpr int kTraceChunks = 64;
+    const bool trace = getenv("SOT_HOST_TRACE") != nullptr;
+    cudaEvent_t tev[4 * kTraceChunks] = {};
+    long long n_traced = 0;
+    if (trace)
+        for (int k = 0; k < 4 * kTraceChunks; ++k) cudaEventCreate(&tev[k]);
 #define SOT_CK(call)                             \
     do {                                         \
         cudaError_t _e = (call);                 \
@@ -488,6 +494,7 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
             HostSlot& s = w.slot[c % kSlots];
             const long long nf = (N - f0 < chunk) ? (N - f0) : chunk;
             if (c >= kSlots) SOT_CK(cudaStreamWaitEvent(w.s_in, s.out_done, 0));  // slot drained
+            if (trace && c < kTraceChunks) SOT_CK(cudaEventRecord(tev[4 * c + 0], w.s_in));
             SOT_CK(cudaMemcpyAsync(s.u, hp->u + f0 * n, 4ULL * nf * n, cudaMemcpyHostToDevice, w.s_in));
             SOT_CK(cudaMemcpyAsync(s.v, hp->v + f0 * m, 4ULL * nf * m, cudaMemcpyHostToDevice, w.s_in));
             if (upstream != nullptr)
@@ -499,6 +506,7 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
                 SOT_CK(cudaMemcpy2DAsync(s.pv, 4ULL * m, hp->pos_v + f0 * hp->pos_v_stride, 4ULL * hp->pos_v_stride,
                                          4ULL * m, nf, cudaMemcpyHostToDevice, w.s_in));
             SOT_CK(cudaEventRecord(s.in_done, w.s_in));
+            if (trace && c < kTraceChunks) SOT_CK(cudaEventRecord(tev[4 * c + 1], w.s_in));
             SOT_CK(cudaStreamWaitEvent(w.s_k, s.in_done, 0));
             sot_problem dp = *hp;
             dp.n_frames = nf;
@@ -518,19 +526,31 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
             }
             SOT_CK(cudaEventRecord(s.k_done, w.s_k));
             SOT_CK(cudaStreamWaitEvent(w.s_out, s.k_done, 0));
+            if (trace && c < kTraceChunks) SOT_CK(cudaEventRecord(tev[4 * c + 2], w.s_out));
             if (loss != nullptr) SOT_CK(cudaMemcpyAsync(loss + f0, s.loss, 4ULL * nf, cudaMemcpyDeviceToHost, w.s_out));
             if (grad_u != nullptr)
                 SOT_CK(cudaMemcpyAsync(grad_u + f0 * n, s.gu, 4ULL * nf * n, cudaMemcpyDeviceToHost, w.s_out));
             if (grad_v != nullptr)
                 SOT_CK(cudaMemcpyAsync(grad_v + f0 * m, s.gv, 4ULL * nf * m, cudaMemcpyDeviceToHost, w.s_out));
             SOT_CK(cudaEventRecord(s.out_done, w.s_out));
+            if (trace && c < kTraceChunks) SOT_CK(cudaEventRecord(tev[4 * c + 3], w.s_out));
         }
+        n_traced = c < kTraceChunks ? c : kTraceChunks;
     }
 done:
     // drain everything that was queued (also on the error path) before the host buffers are reused
     if (w.s_out) cudaStreamSynchronize(w.s_out);
     if (w.s_k) cudaStreamSynchronize(w.s_k);
     if (w.s_in) cudaStreamSynchronize(w.s_in);
+    if (trace) {  // SOT_HOST_TRACE=1: when each chunk's H2D / D2H copies started and ended (ms since the first copy)
+        for (long long k = 0; k < n_traced && rc == SOT_OK; ++k) {
+            float t[4] = {0, 0, 0, 0};
+            for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[4 * k + j]);
+            fprintf(stderr, "sot_loss_grad_host chunk %lld: h2d %.3f..%.3f  d2h %.3f..%.3f ms\n", k, t[0], t[1], t[2], t[3]);
+        }
+        for (int k = 0; k < 4 * kTraceChunks; ++k)
+            if (tev[k]) cudaEventDestroy(tev[k]);
+    }
 #undef SOT_CK
     return rc;
 }
