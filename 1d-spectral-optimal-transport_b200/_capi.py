@@ -63,6 +63,9 @@ SIGNATURES = {
     "sot_mss_backward_device": (ctypes.c_int, [_V, _V, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int32,
                                                ctypes.c_float, _V, _V, _V, _V]),
 }
+SIGNATURES["sot_p2p_mailbox_doubles"] = (ctypes.c_int, [ctypes.c_int32])
+SIGNATURES["sot_p2p_allreduce_device"] = (ctypes.c_int, [_V, _V, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
+                                                         ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _V])
 SOT_MSS_L1, SOT_MSS_L2 = 0, 1
 
 _lib = None
@@ -348,3 +351,20 @@ def mss_backward(zt, zv, mag_weight, logmag_weight, loss_type, post_scale, scale
                                            int(loss_type), float(post_scale), _ptr(scale), _ptr(gt), _ptr(gv),
                                            _stream(zt.device)))
     return gt, gv
+
+
+def p2p_mailbox_doubles(world: int) -> int:
+    return load().sot_p2p_mailbox_doubles(int(world))
+
+
+def p2p_allreduce(values, out, mailbox_ptrs, rank: int, seq: int):
+    """out[:] = sum over ranks of `values` (float64, <= 8 elements) through peer-mapped mailboxes."""
+    lib = load()
+    if values.dtype != torch.float64 or out.dtype != torch.float64 or not values.is_cuda or not out.is_cuda:
+        raise TypeError("sot_b200: p2p_allreduce works on CUDA float64 tensors")
+    world = len(mailbox_ptrs)
+    arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in mailbox_ptrs])
+    with torch.cuda.device(values.device):
+        _check(lib.sot_p2p_allreduce_device(_ptr(values), _ptr(out), values.numel(), arr, world, int(rank), int(seq),
+                                            _stream(values.device)))
+    return out

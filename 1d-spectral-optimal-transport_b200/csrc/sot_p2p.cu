@@ -1,0 +1,113 @@
+// One-shot all-reduce of a few doubles over NVLink / NVSwitch peer memory -- the only exchange the frame-sharded
+// SOT loss has (sum of the per-rank loss sums and frame counts).  It sits between the forward and
+// the backward launch of a ~0.75 ms step, so its latency is what multi-GPU scaling loses; a tiny kernel that
+// stores into every peer's mailbox and spins on its own costs a few microseconds where an NCCL all-reduce
+// (launch + protocol) costs tens.
+//
+// Mailbox (one per rank, symmetric allocation, peers mapped): [world][2 phases][kMaxVals + 1] doubles; entry
+// [r][ph][kMaxVals] is the sequence number rank r wrote last into phase ph.  Call number `seq` (1, 2, ...) uses
+// phase seq & 1: a rank can only start call seq + 2 (same phase) after every peer has written call seq + 1, i.e.
+// after every peer has finished reading call seq -- so two phases are enough.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/sot_b200.h"
+
+namespace sot {
+
+constexpr int kP2PMaxWorld = 16;
+constexpr int kP2PMaxVals = 8;
+constexpr int kP2PSlot = kP2PMaxVals + 1;  // doubles per (rank, phase)
+
+struct P2PArgs {
+    double* mailbox[kP2PMaxWorld];  // mailbox[r] = rank r's mailbox as mapped into this process
+    const double* in;
+    double* out;
+    int count, world, rank;
+    unsigned long long seq;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) {
+    const int t = threadIdx.x;
+    const int phase = static_cast<int>(a.seq & 1ULL);
+    const double seq_val = static_cast<double>(a.seq);
+    __shared__ int failed;
+    if (t == 0) failed = 0;
+    __syncwarp();
+    if (t < a.world) {
+        // my values, then my sequence number, into slot [rank][phase] of peer t's mailbox
+        double* dst = a.mailbox[t] + (static_cast<long long>(a.rank) * 2 + phase) * kP2PSlot;
+        for (int i = 0; i < a.count; ++i) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + i), "d"(a.in[i]) : "memory");
+        __threadfence_system();
+        asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + kP2PMaxVals), "d"(seq_val) : "memory");
+        // wait for rank t's contribution in my own mailbox
+        const double* src = a.mailbox[a.rank] + (static_cast<long long>(t) * 2 + phase) * kP2PSlot;
+        const unsigned long long t0 = global_ns();
+        double seen;
+        do {
+            asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(seen) : "l"(src + kP2PMaxVals) : "memory");
+            if (seen != seq_val && global_ns() - t0 > a.timeout_ns) {
+                failed = 1;  // a peer never arrived: poison the result instead of hanging the GPU
+                break;
+            }
+        } while (seen != seq_val);
+    }
+    __syncwarp();
+    if (t < a.count) {
+        double s = 0.0;
+        for (int r = 0; r < a.world; ++r) {  // fixed order: every rank gets the same bits
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];"
+                         : "=d"(v)
+                         : "l"(a.mailbox[a.rank] + (static_cast<long long>(r) * 2 + phase) * kP2PSlot + t)
+                         : "memory");
+            s += v;
+        }
+        a.out[t] = failed ? __longlong_as_double(0x7ff8000000000000LL) : s;
+    }
+}
+
+}  // namespace sot
+
+extern "C" {
+
+int sot_mss_launch_count_add(void);
+int sot_mss_fail(int code, const char* msg);
+
+int sot_p2p_mailbox_doubles(int32_t world) { return world * 2 * sot::kP2PSlot; }
+
+int sot_p2p_allreduce_device(const double* in, double* out, int32_t count, void* const* mailboxes, int32_t world,
+                             int32_t rank, uint64_t seq, void* stream) {
+    if (in == nullptr || out == nullptr || mailboxes == nullptr)
+        return sot_mss_fail(SOT_EINVAL, "sot_p2p_allreduce_device: NULL pointer");
+    if (count < 1 || count > sot::kP2PMaxVals || world < 1 || world > sot::kP2PMaxWorld || rank < 0 || rank >= world ||
+        seq == 0)
+        return sot_mss_fail(SOT_EINVAL, "sot_p2p_allreduce_device: bad count / world / rank / seq");
+    sot::P2PArgs a{};
+    for (int r = 0; r < world; ++r) {
+        if (mailboxes[r] == nullptr) return sot_mss_fail(SOT_EINVAL, "sot_p2p_allreduce_device: NULL mailbox");
+        a.mailbox[r] = static_cast<double*>(mailboxes[r]);
+    }
+    a.in = in;
+    a.out = out;
+    a.count = count;
+    a.world = world;
+    a.rank = rank;
+    a.seq = seq;
+    a.timeout_ns = 2000000000ULL;  // 2 s
+    sot::sot_p2p_allreduce_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sot_mss_fail(static_cast<int>(e), cudaGetErrorString(e));
+    sot_mss_launch_count_add();
+    return SOT_OK;
+}
+
+}  // extern "C"

@@ -246,10 +246,14 @@ class _SotMean(torch.autograd.Function):
         count = float(u.shape[0])
         ctx.p, ctx.flags = p, flags
         ctx.need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        peer = hasattr(group, "all_reduce") and hasattr(group, "world")  # sharding.PeerReducer (NVLink mailboxes)
         if group is not _LOCAL_ONLY and dist.is_available() and dist.is_initialized() and \
-                dist.get_world_size(group) > 1:
+                (group.world if peer else dist.get_world_size(group)) > 1:
             stats = torch.cat((total, torch.full_like(total, count)))
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+            if peer:
+                stats = group.all_reduce(stats)
+            else:
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
             ctx.count = None
             ctx.save_for_backward(u, v, pos_u, pos_v, stats[1:2])
             return (stats[0] / stats[1]).to(torch.float32)

@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=65536, help="frames per GPU (weak scaling)")
     ap.add_argument("--mode", default=None, choices=["recompute", "fused"], help="backward mode (default: library default)")
     ap.add_argument("--tuning", default=None, help="threads_per_frame,bins_per_thread[,chains] kernel override")
+    ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="the scalar all-reduce of the sharded mean: NCCL or the NVLink peer-memory kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=1024, help="frames per CPU-baseline step (64 signals x 16)")
@@ -134,7 +136,7 @@ def main():
     config = {"workload": args.workload, "frames_per_gpu": args.frames, "bins": F, "p": 2, "square_dist": True,
               "cutoff": cut, "positions": grid, "grads": "both spectra",
               "l2": "inputs+grads per GPU ~%.0f MB >> 126 MB L2, no flush needed" % (16 * F * args.frames / 1e6),
-              "parallelism": f"frames sharded over {world} rank(s), one scalar all-reduce"}
+              "parallelism": f"frames sharded over {world} rank(s), one scalar all-reduce ({args.collective})"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -170,7 +172,7 @@ def main():
     kw = dict(p=2, square_dist=True, dont_normalize=cut, limit_quantile_range=cut)
     if args.mode:
         kw["backward_mode"] = args.mode
-    loss_fn = sharding.ShardedWasserstein1D(**kw)
+    loss_fn = sharding.ShardedWasserstein1D(collective=args.collective, **kw)
     xg = x.clone().requires_grad_(True)
     yg = y.clone().requires_grad_(True)
 

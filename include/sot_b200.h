@@ -160,6 +160,15 @@ int sot_mss_backward_device(const float* zt, const float* zv, int64_t count, flo
                             int32_t loss_type, float post_scale, const float* scale, float* grad_zt, float* grad_zv,
                             void* stream);
 
+/* ---- The one exchange of the frame-sharded loss: all-reduce (sum) of `count` <= 8 doubles over
+ * NVLink / NVSwitch peer memory, one tiny kernel per call.  `mailboxes[r]` = rank r's mailbox as mapped into this
+ * process (a symmetric allocation of sot_p2p_mailbox_doubles(world) doubles per rank, zero-initialised before the
+ * first call; e.g. torch.distributed._symmetric_memory), `seq` = 1, 2, 3, ... the same on every rank.  Every rank
+ * receives bit-identical sums.  A peer that does not arrive within 2 s poisons the result with NaN (no hang). */
+int sot_p2p_mailbox_doubles(int32_t world);
+int sot_p2p_allreduce_device(const double* in, double* out, int32_t count, void* const* mailboxes, int32_t world,
+                             int32_t rank, uint64_t seq, void* stream);
+
 /* Tuning override for benchmarking: threads per frame (32/64/128/256), bins per thread (odd) and
  * merge chains per thread (1/2, 0 = any); 0, 0, 0 restores the built-in choice.  Returns SOT_EINVAL
  * if that combination is not compiled in. */

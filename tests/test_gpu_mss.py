@@ -113,3 +113,21 @@ def test_training_step_example_reduces_the_loss():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["last_loss"] < line["first_loss"] and line["frames_per_s"] > 0
+
+
+def test_peer_memory_all_reduce_matches_nccl():
+    """tools/p2p_check.py on 2 GPUs: the NVLink mailbox all-reduce against NCCL, bit for bit, and the sharded loss
+    with either collective.  Needs two GPUs on the box (skipped otherwise)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "p2p_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["values_match_nccl"] is True
