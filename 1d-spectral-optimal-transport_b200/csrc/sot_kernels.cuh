@@ -1,17 +1,19 @@
-// SOT frame kernel (v3): per-frame 1-D Wasserstein (W_p^p) between two spectra, forward and
+// SOT frame kernel: per-frame 1-D Wasserstein (W_p^p) between two spectra, forward and
 // fused forward+backward.  ONE FRAME PER CTA of TPF threads, persistent grid, many CTAs per SM.
 //
 // Reference semantics reproduced (file:line into /root/reference):
 //   losses.py:172-184  square, mass, safe_divide (cut mode divides the prediction by the
 //                      TARGET's mass), utils.py:135-142
-//   losses.py:292-293  inclusive CDFs                     -> fp64 block scan, fp32 storage
+//   losses.py:292-293  inclusive CDFs                     -> packed-fp32 local prefix sums, fp64 scan of the
+//                                                           per-thread sums (raw weights: fp64 per entry)
 //   losses.py:295      sort(cat(cu, cv))                  -> merge-path partition + sequential walk
 //   losses.py:214-220  searchsorted-left + clamp + gather -> running co-ranks of the walk
 //   losses.py:301-313  sum_k dq_k * |uq_k - vq_k|^p, strict `qs > 1` mask
 //   autograd of all of the above          -> dL/dCDF array, suffix scans,
 //                                                           normalisation chain rule, 2x
 //
-// Shared memory: rows of RS floats at COMPILE-TIME offsets, so that for a CDF entry at shared
+// Shared memory: first the small per-CTA structures (scan scratch, first-slot mailbox + carry per
+// chunk, mbarrier), then rows of RS floats at COMPILE-TIME offsets, so that for a CDF entry at shared
 // address a its support position is at a + POS_OFF and its dL/dCDF at a + G_OFF (immediates):
 //   rows 0, 1 : CDF of u / v, entry [n] / [m] = +inf sentinel
 //   rows 2, 3 : support positions of u / v, entry [n] / [m] repeats the last one (the reference's
@@ -26,7 +28,7 @@
 //   next 4    : (complex input, template flag CPLX) the two interleaved complex64 STFT rows: the
 //               magnitude (squared) is formed while they are read -- no |.| tensor in HBM -- and the
 //               gradient kernel overwrites them in place with the complex gradient rows
-//   then      : scan scratch, first-slot mailbox + carry per chunk, mbarrier
+//   then      : padding (threads whose bins lie past the end of a row read, and mask, what follows)
 // The raw rows of a frame arrive by TMA bulk copy (`cp.async.bulk`, SASS UBLKCP).  A 4*n-byte row
 // is only 4-byte aligned (n = 1025 / 257), the bulk unit is 16 bytes: the copy therefore fetches
 // the 16-byte aligned WINDOW around the row and the kernel skips the `lead` bytes in front.  The
@@ -35,7 +37,9 @@
 // Gradient rows leave the same way: written over the dL/dCDF rows at the row's own 16-byte phase,
 // bulk store of the aligned middle, <= 3 scalar stores per edge.
 // Thread t owns the E consecutive bins [t*E, t*E+E) of both rows ("blocked"); E is odd so every
-// blocked access of a warp is bank-conflict free.
+// blocked access of a warp is bank-conflict free.  Everything elementwise runs on (u, v) PAIRS in
+// packed fp32x2 instructions (FFMA2 / FADD2 / FMUL2); the merge walk keeps its selects and masks on
+// the fma pipe (predicated FFMA, FFMA.SAT) because the alu pipe runs at half rate.
 #pragma once
 #include <type_traits>
 
