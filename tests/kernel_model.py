@@ -153,3 +153,40 @@ def frame_loss_and_grads(x, y, pu, pv, p, square, cut_scale, limit, T, L):
     gx = (F32(2) * x * ga).astype(F32) if square else ga
     gy = (F32(2) * y * gb).astype(F32) if square else gb
     return loss, gx, gy, cu, cv, g_cu, g_cv
+
+
+def cdf_stage_model(x, threads, per_thread, mass_floor=EPS, square=True):
+    """Model of the kernel's CDF stage (csrc/sot_kernels.cuh, stage 2) for one row `x` (float32):
+    thread t owns bins [t*E, t*E+E); local fp32 prefix sums (x^2 fused into the add); the per-thread sums
+    are added up in fp64 -> exclusive offsets; entry = fl32(head + fl32(prefix * inv32 + tail)) where
+    (head, tail) is the fp32 split of offset * inv64; every entry is capped by the next thread's head.
+    Returns the float32 CDF row.  (fl32(x*x + acc) is formed in float64 and rounded once: x*x is exact there.)"""
+    n = len(x)
+    E = per_thread
+    xs = np.zeros(threads * E, np.float64)
+    xs[:n] = np.asarray(x, np.float32).astype(np.float64)
+    local = np.zeros((threads, E), np.float32)
+    for t in range(threads):
+        acc = F32(0.0)
+        for c in range(E):
+            v = xs[t * E + c]
+            acc = F32((v * v if square else v) + np.float64(acc))
+            local[t, c] = acc
+    totals = local[:, -1].astype(np.float64)
+    offsets = np.concatenate(([0.0], np.cumsum(totals)))  # offsets[t] exclusive, offsets[threads] = total
+    mass = F32(offsets[-1])
+    inv64 = 1.0 / np.float64(mass if mass > mass_floor else mass_floor)
+    inv32 = F32(inv64)
+    out = np.zeros(n, np.float32)
+    for t in range(threads):
+        base = offsets[t] * inv64
+        head = F32(base)
+        tail = F32(base - np.float64(head))
+        cap = F32(offsets[t + 1] * inv64)
+        for c in range(E):
+            i = t * E + c
+            if i >= n:
+                break
+            inner = F32(np.float64(local[t, c]) * np.float64(inv32) + np.float64(tail))  # one FFMA
+            out[i] = min(F32(head + inner), cap)
+    return out

@@ -97,3 +97,24 @@ def test_end_to_end_model_vs_stable_autograd(cut):
             e_ref = np.linalg.norm(ref32 - truth) / np.linalg.norm(truth)
             assert e_mine <= max(2e-6, 1.5 * e_ref), (r, e_mine, e_ref)
     assert same_cdf >= x.shape[0] // 4, f"only {same_cdf} frames reproduced the reference CDFs"
+
+
+@pytest.mark.parametrize("threads,per_thread,n", [(64, 17, 1025), (32, 9, 257), (128, 17, 2049), (32, 33, 1025)])
+def test_cdf_stage_model_is_monotone_and_tracks_fp64(threads, per_thread, n):
+    """The design argument of the packed-fp32 CDF stage, checked on the CPU model for adversarial rows: the row is
+    non-decreasing across thread boundaries (the cap by the next thread's head), ends at fl32(total / mass), and
+    stays within ~E/2 ulp of the float64 CDF."""
+    rng = np.random.default_rng(threads * 1000 + n)
+    rows = [np.exp(6.0 * rng.standard_normal(n) - 8.0), rng.random(n), np.full(n, 0.37),
+            np.where(rng.random(n) < 0.02, 1.0, 1e-7 * rng.random(n)),   # isolated peaks over a noise floor
+            np.concatenate((np.full(n - 1, 1e-12), [1.0])), np.concatenate(([1.0], np.full(n - 1, 1e-9)))]
+    for x in rows:
+        x = x.astype(np.float32)
+        c = KM.cdf_stage_model(x, threads, per_thread)
+        assert np.all(np.diff(c) >= 0), "CDF must be non-decreasing"
+        w = x.astype(np.float64) ** 2
+        mass = max(float(np.float32(w.sum())), 1e-7)  # utils.py:135-142: a mass <= eps is replaced by eps
+        c64 = np.cumsum(w) / mass
+        ulp = np.spacing(c64.astype(np.float32))
+        assert np.max(np.abs(c.astype(np.float64) - c64) / ulp) <= per_thread / 2 + 2
+        assert abs(float(c[-1]) - c64[-1]) <= 1.2e-7 * c64[-1]
