@@ -100,6 +100,11 @@ class ShardedWasserstein1D(losses.Wasserstein1D):
         self.collective = collective
         self._reducer = None
 
+    def __getstate__(self):  # the peer-memory mailboxes belong to this process: never pickled with the module
+        state = self.__dict__.copy()
+        state["_reducer"] = None
+        return state
+
     def _mean_group(self):
         if self.collective == "nccl" or not (dist.is_available() and dist.is_initialized()):
             return self.process_group

@@ -61,3 +61,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_sharded_module_pickles_without_its_peer_memory_mailboxes():
+    import io
+    import pickle
+    from sot_b200 import sharding
+    mod = sharding.ShardedWasserstein1D(p=2, square_dist=True, fixed_x=65, collective="auto")
+    mod._reducer = object()  # stands in for a live PeerReducer (CUDA tensors + symmetric-memory handle)
+    clone = pickle.loads(pickle.dumps(mod))
+    assert clone._reducer is None and clone.collective == "auto" and clone.fixed_x.shape == (65,)
+    buf = io.BytesIO()
+    torch.save(mod, buf)
+    buf.seek(0)
+    assert torch.load(buf, weights_only=False)._reducer is None
+    with pytest.raises(ValueError):
+        sharding.ShardedWasserstein1D(collective="mpi")
