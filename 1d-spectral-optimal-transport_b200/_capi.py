@@ -66,6 +66,8 @@ SIGNATURES = {
 SIGNATURES["sot_p2p_mailbox_doubles"] = (ctypes.c_int, [ctypes.c_int32])
 SIGNATURES["sot_p2p_allreduce_device"] = (ctypes.c_int, [_V, _V, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
                                                          ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _V])
+SIGNATURES["sot_p2p_global_mean_device"] = (ctypes.c_int, [_V, ctypes.c_double, _V, _V, ctypes.POINTER(ctypes.c_void_p),
+                                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _V])
 SOT_MSS_L1, SOT_MSS_L2 = 0, 1
 
 _lib = None
@@ -368,3 +370,18 @@ def p2p_allreduce(values, out, mailbox_ptrs, rank: int, seq: int):
         _check(lib.sot_p2p_allreduce_device(_ptr(values), _ptr(out), values.numel(), arr, world, int(rank), int(seq),
                                             _stream(values.device)))
     return out
+
+
+def p2p_global_mean(local_sum, local_count: float, mailbox_ptrs, rank: int, seq: int):
+    """(mean, 1 / count) over all ranks as two (1,) float32 tensors from this rank's (1,) float64 sum and its count."""
+    lib = load()
+    if local_sum.dtype != torch.float64 or not local_sum.is_cuda or local_sum.numel() != 1:
+        raise TypeError("sot_b200: p2p_global_mean takes a (1,) CUDA float64 sum")
+    out = torch.empty(2, dtype=torch.float32, device=local_sum.device)
+    world = len(mailbox_ptrs)
+    arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in mailbox_ptrs])
+    with torch.cuda.device(local_sum.device):
+        _check(lib.sot_p2p_global_mean_device(_ptr(local_sum), float(local_count), _ptr(out),
+                                              ctypes.c_void_p(out.data_ptr() + 4), arr, world, int(rank), int(seq),
+                                              _stream(local_sum.device)))
+    return out[0:1], out[1:2]

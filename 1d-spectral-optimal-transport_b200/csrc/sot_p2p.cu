@@ -24,6 +24,11 @@ struct P2PArgs {
     double* mailbox[kP2PMaxWorld];  // mailbox[r] = rank r's mailbox as mapped into this process
     const double* in;
     double* out;
+    // global-mean form (the sharded loss): values = (*in, local_count); results mean_out = sum / count and
+    // inv_count_out = 1 / count as floats, ready for the caller -- no scalar-sized torch kernels around the exchange
+    double local_count;
+    float* mean_out;
+    float* inv_count_out;
     int count, world, rank;
     unsigned long long seq;
     unsigned long long timeout_ns;
@@ -45,7 +50,10 @@ __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) 
     if (t < a.world) {
         // my values, then my sequence number, into slot [rank][phase] of peer t's mailbox
         double* dst = a.mailbox[t] + (static_cast<long long>(a.rank) * 2 + phase) * kP2PSlot;
-        for (int i = 0; i < a.count; ++i) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + i), "d"(a.in[i]) : "memory");
+        for (int i = 0; i < a.count; ++i) {
+            const double v = (a.mean_out != nullptr && i == 1) ? a.local_count : a.in[i];
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + i), "d"(v) : "memory");
+        }
         __threadfence_system();
         asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + kP2PMaxVals), "d"(seq_val) : "memory");
         // wait for rank t's contribution in my own mailbox
@@ -71,7 +79,15 @@ __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) 
                          : "memory");
             s += v;
         }
-        a.out[t] = failed ? __longlong_as_double(0x7ff8000000000000LL) : s;
+        s = failed ? __longlong_as_double(0x7ff8000000000000LL) : s;
+        if (a.out != nullptr) a.out[t] = s;
+        if (a.mean_out != nullptr) {  // t = 0 holds the sum, t = 1 the count
+            const double cnt = __shfl_sync((1u << a.count) - 1u, s, 1);
+            if (t == 0) {
+                *a.mean_out = static_cast<float>(s / cnt);
+                *a.inv_count_out = static_cast<float>(1.0 / cnt);
+            }
+        }
     }
 }
 
@@ -84,21 +100,43 @@ int sot_mss_fail(int code, const char* msg);
 
 int sot_p2p_mailbox_doubles(int32_t world) { return world * 2 * sot::kP2PSlot; }
 
+static int p2p_launch(sot::P2PArgs& a, void* const* mailboxes, int32_t world, int32_t rank, uint64_t seq, void* stream);
+
+int sot_p2p_global_mean_device(const double* local_sum, double local_count, float* mean_out, float* inv_count_out,
+                               void* const* mailboxes, int32_t world, int32_t rank, uint64_t seq, void* stream) {
+    if (local_sum == nullptr || mean_out == nullptr || inv_count_out == nullptr || mailboxes == nullptr)
+        return sot_mss_fail(SOT_EINVAL, "sot_p2p_global_mean_device: NULL pointer");
+    sot::P2PArgs a{};
+    a.in = local_sum;
+    a.local_count = local_count;
+    a.mean_out = mean_out;
+    a.inv_count_out = inv_count_out;
+    a.count = 2;
+    return p2p_launch(a, mailboxes, world, rank, seq, stream);
+}
+
 int sot_p2p_allreduce_device(const double* in, double* out, int32_t count, void* const* mailboxes, int32_t world,
                              int32_t rank, uint64_t seq, void* stream) {
     if (in == nullptr || out == nullptr || mailboxes == nullptr)
         return sot_mss_fail(SOT_EINVAL, "sot_p2p_allreduce_device: NULL pointer");
+    if (count < 1 || count > sot::kP2PMaxVals)
+        return sot_mss_fail(SOT_EINVAL, "sot_p2p_allreduce_device: bad count");
+    sot::P2PArgs a{};
+    a.in = in;
+    a.out = out;
+    a.count = count;
+    return p2p_launch(a, mailboxes, world, rank, seq, stream);
+}
+
+static int p2p_launch(sot::P2PArgs& a, void* const* mailboxes, int32_t world, int32_t rank, uint64_t seq, void* stream) {
+    const int32_t count = a.count;
     if (count < 1 || count > sot::kP2PMaxVals || world < 1 || world > sot::kP2PMaxWorld || rank < 0 || rank >= world ||
         seq == 0)
         return sot_mss_fail(SOT_EINVAL, "sot_p2p_allreduce_device: bad count / world / rank / seq");
-    sot::P2PArgs a{};
     for (int r = 0; r < world; ++r) {
         if (mailboxes[r] == nullptr) return sot_mss_fail(SOT_EINVAL, "sot_p2p_allreduce_device: NULL mailbox");
         a.mailbox[r] = static_cast<double*>(mailboxes[r]);
     }
-    a.in = in;
-    a.out = out;
-    a.count = count;
     a.world = world;
     a.rank = rank;
     a.seq = seq;

@@ -249,11 +249,15 @@ class _SotMean(torch.autograd.Function):
         peer = hasattr(group, "all_reduce") and hasattr(group, "world")  # sharding.PeerReducer (NVLink mailboxes)
         if group is not _LOCAL_ONLY and dist.is_available() and dist.is_initialized() and \
                 (group.world if peer else dist.get_world_size(group)) > 1:
+            if peer:  # one kernel: exchange over NVLink, mean and 1/count come back as floats
+                mean, inv_count = group.global_mean(total, count)
+                ctx.count = None
+                ctx.inv_count = True
+                ctx.save_for_backward(u, v, pos_u, pos_v, inv_count)
+                return mean[0]
+            ctx.inv_count = False
             stats = torch.cat((total, torch.full_like(total, count)))
-            if peer:
-                stats = group.all_reduce(stats)
-            else:
-                dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
             ctx.count = None
             ctx.save_for_backward(u, v, pos_u, pos_v, stats[1:2])
             return (stats[0] / stats[1]).to(torch.float32)
@@ -264,7 +268,10 @@ class _SotMean(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        if ctx.count is None:
+        if ctx.count is None and ctx.inv_count:
+            u, v, pos_u, pos_v, inv_count = ctx.saved_tensors
+            scale = (grad_out.to(torch.float32) * inv_count).reshape(1)
+        elif ctx.count is None:
             u, v, pos_u, pos_v, count = ctx.saved_tensors
             scale = (grad_out.to(torch.float64) / count).to(torch.float32).reshape(1)
         else:

@@ -45,6 +45,11 @@ class PeerReducer:
         self.seq += 1
         return _capi.p2p_allreduce(values, torch.empty_like(values), self.ptrs, self.rank, self.seq)
 
+    def global_mean(self, local_sum: torch.Tensor, local_count: float):
+        """(sum over ranks of local_sum) / (sum of local_count) and 1 / (sum of local_count), (1,) float32 each."""
+        self.seq += 1
+        return _capi.p2p_global_mean(local_sum, local_count, self.ptrs, self.rank, self.seq)
+
 
 class _GlobalMean(torch.autograd.Function):
     """mean over the frames of ALL ranks of per-rank rows; differentiable w.r.t. the local rows."""

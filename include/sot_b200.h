@@ -166,6 +166,11 @@ int sot_mss_backward_device(const float* zt, const float* zv, int64_t count, flo
  * first call; e.g. torch.distributed._symmetric_memory), `seq` = 1, 2, 3, ... the same on every rank.  Every rank
  * receives bit-identical sums.  A peer that does not arrive within 2 s poisons the result with NaN (no hang). */
 int sot_p2p_mailbox_doubles(int32_t world);
+/* The form the sharded loss uses: exchanges (*local_sum, local_count) and writes the global mean sum / count and
+ * 1 / count as floats (device memory) -- the forward value and the backward's scale, no scalar-sized kernels around
+ * the exchange. */
+int sot_p2p_global_mean_device(const double* local_sum, double local_count, float* mean_out, float* inv_count_out,
+                               void* const* mailboxes, int32_t world, int32_t rank, uint64_t seq, void* stream);
 int sot_p2p_allreduce_device(const double* in, double* out, int32_t count, void* const* mailboxes, int32_t world,
                              int32_t rank, uint64_t seq, void* stream);
 

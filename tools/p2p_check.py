@@ -51,7 +51,8 @@ def main():
         v = fn(xg, yg, x_pos=pos, y_pos=pos)
         v.backward()
         out[coll] = (v.item(), yg.grad.clone())
-    same = out["nccl"][0] == out["p2p"][0] and torch.equal(out["nccl"][1], out["p2p"][1])
+    # same loss bits; the gradients' upstream scale is grad * fl32(1/N) on one path and fl32(grad / N) on the other
+    same = out["nccl"][0] == out["p2p"][0] and torch.allclose(out["nccl"][1], out["p2p"][1], rtol=1e-6, atol=0)
     flag = torch.tensor([float(ok and same)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
