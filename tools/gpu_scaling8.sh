@@ -1,10 +1,10 @@
 #!/bin/bash
-# 8-GPU weak-scaling step with either collective (NCCL all-reduce vs the peer-memory kernel), two runs each
+# 8-GPU weak-scaling step with either collective (peer-memory kernel vs NCCL all-reduce)
 mkdir -p gpurun_out
 : > gpurun_out/scaling8.jsonl
 NG=$(nvidia-smi -L | wc -l)
-for c in nccl p2p nccl p2p; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
+for c in ${COLLECTIVES:-p2p nccl p2p}; do
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
     bench.py --gpus $NG --steps 30 --warmup 5 --no-e2e --no-cpu --collective $c 2>/dev/null | grep '^{' | tail -1 >> gpurun_out/scaling8.jsonl
 done
 python - <<'PY'
