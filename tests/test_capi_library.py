@@ -61,3 +61,51 @@ def test_sass_contains_tma_bulk_copies():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run(["cuobjdump", "-sass", _capi.library_path()], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass
+
+
+def _build_c_demo(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from sot_b200 import _capi
+    _capi.load()
+    lib_dir = os.path.dirname(_capi.library_path())
+    exe = os.path.join(str(tmp_path), "sot_c_demo")
+    cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-Werror", os.path.join(ROOT, "examples", "c_abi_demo.c"),
+           "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lsot_b200", "-Wl,-rpath," + lib_dir, "-lm", "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_plain_c_caller_compiles_and_links_against_the_header(tmp_path):
+    """The boundary is usable from C: examples/c_abi_demo.c builds with -Wall -Werror against include/sot_b200.h."""
+    assert os.path.exists(_build_c_demo(tmp_path))
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_gives_the_python_layers_numbers(tmp_path):
+    import json
+    import subprocess
+    import numpy as np
+    import torch
+    from sot_b200 import losses
+    out = subprocess.run([_build_c_demo(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    n_frames, n_bins = 64, 1025
+    pos = np.arange(n_bins, dtype=np.float32) / np.float32(n_bins - 1)
+    f = np.arange(n_frames, dtype=np.float64)[:, None]
+    cx = 0.30 + 0.004 * f
+    x = np.exp(-0.25 * (pos.astype(np.float64)[None] - cx) ** 2 / 0.02 ** 2).astype(np.float32)
+    y = (0.7 * np.exp(-0.25 * (pos.astype(np.float64)[None] - cx - 0.05) ** 2 / 0.02 ** 2)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    yt = torch.from_numpy(y).cuda().requires_grad_(True)
+    rows = losses.sot_frames(xt, yt, torch.from_numpy(pos).cuda(), torch.from_numpy(pos).cuda(), p=2, square=True)
+    rows.sum().backward()
+    assert line["frames"] == n_frames and line["launches"] >= 1
+    assert abs(line["mean_loss"] - rows.mean().item()) <= 2e-6 * rows.mean().item()  # (libm exp vs numpy exp inputs)
+    assert abs(line["mean_loss"] - 0.0025) <= 1e-4  # two unit-mass Gaussians 0.05 apart: W_2^2 = 0.05^2
+    want = (xt.grad.abs().sum() + yt.grad.abs().sum()).item()
+    assert abs(line["grad_abs_sum"] - want) <= 1e-4 * want
