@@ -10,7 +10,7 @@ What is the reference's and what is a stand-in:
     its DDSP synthesiser are outside the hot path and are not reproduced): a small 1-D CNN over log-magnitude frames
     with a soft-argmax pitch head, and a stationary harmonic oscillator bank.
 
-    python examples/train_step.py [--steps 30] [--signals 256]
+    python examples/train_step.py [--steps 30] [--batch 256]
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_step.py
 Prints one JSON line: steps/s, frames/s (16 frames per signal), first and last loss.
 """
@@ -64,7 +64,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--signals", type=int, default=256, help="signals per GPU and step (16 frames each)")
+    ap.add_argument("--batch", dest="signals", type=int, default=256, help="signals per GPU and step (16 frames each)")
     ap.add_argument("--lr", type=float, default=1e-4, help="Adam learning rate (paper config: 1e-4)")
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))

@@ -107,7 +107,7 @@ def test_training_step_example_reduces_the_loss():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "examples", "train_step.py"), "--steps", "60", "--signals", "32",
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "train_step.py"), "--steps", "60", "--batch", "32",
                           "--lr", "1e-3"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
