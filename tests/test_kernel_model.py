@@ -118,3 +118,29 @@ def test_cdf_stage_model_is_monotone_and_tracks_fp64(threads, per_thread, n):
         ulp = np.spacing(c64.astype(np.float32))
         assert np.max(np.abs(c.astype(np.float64) - c64) / ulp) <= per_thread / 2 + 2
         assert abs(float(c[-1]) - c64[-1]) <= 1.2e-7 * c64[-1]
+
+
+def test_cutoff_mask_on_the_fma_pipe_is_exactly_zero_or_one():
+    """The walk replaces `q > 1 ? 0 : x` by x * keep(q), keep(q) = sat(fma(q, -2^60, thr+ * 2^60)) with thr+ the
+    float after 1 (csrc/sot_kernels.cuh, `keep_c`).  Model of that FFMA.SAT (the product and the sum are exact in
+    float64 for float32 operands this close to 1, one rounding to float32, clamp to [0, 1]): keep is exactly 1 for
+    every float32 q <= 1 and exactly 0 for every q > 1, including the neighbours of 1, zero, denormals, huge values
+    and +inf; without a limit the constant is +inf and keep is 1 for every finite q."""
+    f32 = np.float32
+    thr_plus = np.nextafter(f32(1.0), f32(2.0))
+    keep_c = np.float64(thr_plus) * 2.0 ** 60
+
+    def keep(q, c):
+        with np.errstate(invalid="ignore", over="ignore"):
+            v = f32(np.float64(q) * -(2.0 ** 60) + c)
+        return f32(0.0) if np.isnan(v) else f32(min(max(v, f32(0.0)), f32(1.0)))
+
+    below = [f32(0.0), f32(1e-45), f32(1e-30), f32(0.5), np.nextafter(f32(1.0), f32(0.0)), f32(1.0)]
+    above = [thr_plus, np.nextafter(thr_plus, f32(2.0)), f32(1.5), f32(1e20), f32(3.4e38), f32(np.inf)]
+    rng = np.random.default_rng(0)
+    below += list(rng.random(2000).astype(np.float32))
+    above += list((1.0 + rng.random(2000) * 1e-3).astype(np.float32) + f32(2e-7))
+    assert all(keep(q, keep_c) == 1.0 for q in below)
+    assert all(keep(q, keep_c) == 0.0 for q in above if q > 1.0)
+    finite = [f32(0.0), f32(1.0), f32(7.0), f32(3.4e38)]
+    assert all(keep(q, np.float64(np.inf)) == 1.0 for q in finite) and keep(f32(np.inf), np.float64(np.inf)) == 0.0
