@@ -14,7 +14,7 @@ import torch
 from . import build as _build
 
 SOT_SQUARE, SOT_CUT_SCALE, SOT_LIMIT, SOT_RAW_WEIGHTS, SOT_UNIFORM_GRID, SOT_COMPLEX_INPUT = 1, 2, 4, 8, 16, 32
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers
 
@@ -36,6 +36,24 @@ class SotProblem(ctypes.Structure):
     ]
 
 
+class SotMeanPlan(ctypes.Structure):
+    """`struct sot_mean_plan` of include/sot_b200.h."""
+    _fields_ = [
+        ("workspace", ctypes.c_void_p),
+        ("mean_out", ctypes.c_void_p),
+        ("mean_scale", ctypes.c_double),
+        ("total_out", ctypes.c_void_p),
+        ("count_value", ctypes.c_double),
+        ("post_mailboxes", ctypes.POINTER(ctypes.c_void_p)),
+        ("post_world", ctypes.c_int32),
+        ("post_rank", ctypes.c_int32),
+        ("post_seq", ctypes.c_uint64),
+        ("post_seq_device", ctypes.c_void_p),
+        ("grad_scale", ctypes.c_float),
+        ("grad_scale_device", ctypes.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); kept in one place so tests can check the exported symbol table
 _P = ctypes.POINTER(SotProblem)
 _V = ctypes.c_void_p
@@ -46,6 +64,8 @@ SIGNATURES = {
     "sot_forward_backward_scaled_device": (ctypes.c_int, [_P, _V, _V, _V, ctypes.c_int32, _V, _V, _V, _V]),
     "sot_coranks_per_frame": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32]),
     "sot_scale_rows_device": (ctypes.c_int, [_V, _V, _V, ctypes.c_int64, ctypes.c_int32, _V]),
+    "sot_mean_step_device": (ctypes.c_int, [_P, ctypes.POINTER(SotMeanPlan), _V, _V, _V, _V]),
+    "sot_scale_inplace_device": (ctypes.c_int, [_V, ctypes.c_int64, _V, ctypes.c_int64, _V, _V]),
     "sot_quantiles_device": (ctypes.c_int, [_P, _V, _V, _V, _V, _V, _V, _V, _V]),
     "sot_quantile_lookup_device": (ctypes.c_int, [_V, _V, _V, _V, ctypes.c_int64, ctypes.c_int32,
                                                   ctypes.c_int32, _V]),
@@ -68,6 +88,9 @@ SIGNATURES["sot_p2p_allreduce_device"] = (ctypes.c_int, [_V, _V, ctypes.c_int32,
                                                          ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _V])
 SIGNATURES["sot_p2p_global_mean_device"] = (ctypes.c_int, [_V, ctypes.c_double, _V, _V, ctypes.POINTER(ctypes.c_void_p),
                                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _V])
+SIGNATURES["sot_p2p_wait_mean_device"] = (ctypes.c_int, [_V, ctypes.c_double, _V, ctypes.POINTER(ctypes.c_void_p),
+                                                         ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _V,
+                                                         ctypes.c_uint32, _V])
 SOT_MSS_L1, SOT_MSS_L2 = 0, 1
 
 _lib = None
@@ -223,6 +246,84 @@ def forward_backward_scaled(u, v, pos_u, pos_v, p, flags, scale, coranks=None, w
     return gu, gv
 
 
+_workspaces: dict = {}  # (device index, stream handle) -> 2 zeroed doubles the mean-step kernel keeps zero
+
+
+def mean_workspace(device) -> torch.Tensor:
+    """The (sum, ticket) accumulator of `sot_mean_step_device` for the current stream of `device`: allocated and
+    zeroed once, left zero by every launch (its last CTA resets it)."""
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(2, dtype=torch.float64, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def mean_step(u, v, pos_u, pos_v, p, flags, grad_scale: float, mean_scale: float, want_gu=True, want_gv=True,
+              want_rows=False, total_out=None, count_value: float = 0.0, post=None, grad_scale_device=None,
+              want_mean=None):
+    """ONE launch: mean over this launch's frames (times `mean_scale` * N, i.e. sum * mean_scale) as a 0-dim float32
+    tensor, and the gradient rows of `grad_scale * sum_n loss_n`.  `total_out`: (2,) float64 tensor that receives
+    (sum, count_value) instead of / besides the mean; `post` = (mailbox pointers, rank, seq): the last CTA also
+    stores (sum, count_value, seq) into every peer's mailbox (seq: an int, or a one-element int64 DEVICE tensor
+    holding the previous call number).  Returns (mean or None, rows or None, gu, gv)."""
+    lib = load()
+    prob = make_problem(u, v, pos_u, pos_v, p, flags)
+    dev = u.device
+    if want_mean is None:
+        want_mean = total_out is None and post is None
+    if grad_scale_device is not None:
+        _dev_tensor(grad_scale_device, "grad_scale_device")
+    mean = torch.empty((), dtype=torch.float32, device=dev) if want_mean else None
+    rows = torch.empty(u.shape[0], dtype=torch.float32, device=dev) if want_rows else None
+    gu = torch.empty_like(u) if want_gu else None
+    gv = torch.empty_like(v) if want_gv else None
+    plan = SotMeanPlan()
+    plan.workspace = mean_workspace(dev).data_ptr()
+    plan.mean_out = None if mean is None else mean.data_ptr()
+    plan.mean_scale = float(mean_scale)
+    plan.total_out = None if total_out is None else total_out.data_ptr()
+    plan.count_value = float(count_value)
+    plan.grad_scale = float(grad_scale)
+    plan.grad_scale_device = None if grad_scale_device is None else grad_scale_device.data_ptr()
+    keep = None
+    if post is not None:
+        ptrs, rank, seq = post
+        keep = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(q)) for q in ptrs])
+        plan.post_mailboxes, plan.post_world, plan.post_rank = keep, len(ptrs), int(rank)
+        if isinstance(seq, torch.Tensor):
+            plan.post_seq, plan.post_seq_device = 0, seq.data_ptr()
+        else:
+            plan.post_seq = int(seq)
+    with torch.cuda.device(dev):
+        _check(lib.sot_mean_step_device(ctypes.byref(prob), ctypes.byref(plan), _ptr(rows), _ptr(gu), _ptr(gv),
+                                        _stream(dev)))
+    return mean, rows, gu, gv
+
+
+def scale_inplace(a, b, scale) -> None:
+    """a *= scale; b *= scale in place (either may be None); `scale` = one-element float32 DEVICE tensor.  The
+    kernel leaves at once when the scalar is exactly 1."""
+    lib = load()
+    _dev_tensor(scale, "scale")
+    if scale.numel() != 1:
+        raise ValueError("sot_b200: the scale must hold one element")
+    dev = scale.device
+    views = []
+    for t in (a, b):
+        if t is None:
+            views.append(None)
+            continue
+        if not t.is_contiguous() or t.device != dev:
+            raise ValueError("sot_b200: rows to scale must be contiguous and on the scale's device")
+        views.append(torch.view_as_real(t) if t.is_complex() else t)
+    va, vb = views
+    with torch.cuda.device(dev):
+        _check(lib.sot_scale_inplace_device(_ptr(va), 0 if va is None else va.numel(), _ptr(vb),
+                                            0 if vb is None else vb.numel(), _ptr(scale), _stream(dev)))
+
+
 def scale_rows(unit, scale) -> torch.Tensor:
     lib = load()
     _dev_tensor(unit, "unit"), _dev_tensor(scale, "scale")
@@ -369,6 +470,24 @@ def p2p_allreduce(values, out, mailbox_ptrs, rank: int, seq: int):
     with torch.cuda.device(values.device):
         _check(lib.sot_p2p_allreduce_device(_ptr(values), _ptr(out), values.numel(), arr, world, int(rank), int(seq),
                                             _stream(values.device)))
+    return out
+
+
+def p2p_wait_mean(mailbox_ptrs, rank: int, seq, expected_count: float = 0.0, status_ptr: int = 0,
+                  timeout_ms: int = 0, device=None) -> torch.Tensor:
+    """Collects call `seq` of every rank from this rank's mailbox (the stores were made by the last CTA of
+    `mean_step(..., post=...)` on every rank) and returns the global mean, a 0-dim float32 tensor."""
+    lib = load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    world = len(mailbox_ptrs)
+    arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(q)) for q in mailbox_ptrs])
+    with torch.cuda.device(dev):
+        on_device = isinstance(seq, torch.Tensor)  # one-element int64 device tensor: the previous call number
+        _check(lib.sot_p2p_wait_mean_device(_ptr(out), float(expected_count),
+                                            ctypes.c_void_p(status_ptr) if status_ptr else None, arr, world,
+                                            int(rank), 0 if on_device else int(seq), _ptr(seq) if on_device else None,
+                                            int(timeout_ms), _stream(dev)))
     return out
 
 

@@ -28,8 +28,20 @@ def _nvcc() -> str:
     return exe
 
 
+# configurations that only `sot_set_tuning` could ever reach: compiled with SOT_BUILD_TUNING=1
+TUNING_ONLY = ("sot_cfg_32_9_296_2", "sot_cfg_64_17_1032_2", "sot_cfg_128_9_1032_1", "sot_cfg_32_33_1064_2",
+               "sot_cfg_32_33_1064_1")
+
+
+def _tuning() -> bool:
+    return os.environ.get("SOT_BUILD_TUNING", "0") not in ("", "0")
+
+
 def _sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    if not _tuning():
+        srcs = [s for s in srcs if os.path.basename(s)[:-3] not in TUNING_ONLY]
+    return srcs
 
 
 def _deps():
@@ -46,7 +58,7 @@ def is_stale() -> bool:
 
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *(["-DSOT_TUNING_CONFIGS"] if _tuning() else []), "-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     with open(obj[:-2] + ".ptxas.log", "w") as f:
         f.write(res.stdout + res.stderr)
@@ -61,17 +73,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
+    # one builder at a time across processes (every rank of a torchrun job can find the library stale at once);
+    # whoever gets the lock second finds it fresh and returns
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
     wanted = {os.path.basename(src)[:-3] for src in _sources()}
     for old in glob.glob(os.path.join(OBJ_DIR, "*")):  # objects of configurations that no longer exist
         if os.path.basename(old).split(".")[0] not in wanted:
             os.remove(old)
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(_compile, _sources()))
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+    cmd = [_nvcc(), "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(f"built {LIB_PATH}", file=sys.stderr)
     return LIB_PATH

@@ -12,32 +12,70 @@
 #include "../../include/sot_b200.h"
 #include "sot_launch.cuh"
 
-SOT_DECLARE_CONFIG(32, 9, 296, 2)
+// Production configurations (one per row-length class).  The alternatives that were only ever reachable through
+// `sot_set_tuning` are compiled in with -DSOT_TUNING_CONFIGS (`SOT_BUILD_TUNING=1 python -m sot_b200.build`).
 SOT_DECLARE_CONFIG(32, 9, 296, 1)
 SOT_DECLARE_CONFIG(64, 9, 584, 2)
-SOT_DECLARE_CONFIG(64, 17, 1032, 2)
 SOT_DECLARE_CONFIG(64, 17, 1032, 1)
-SOT_DECLARE_CONFIG(128, 9, 1032, 1)
-SOT_DECLARE_CONFIG(32, 33, 1064, 2)
-SOT_DECLARE_CONFIG(32, 33, 1064, 1)
 SOT_DECLARE_CONFIG(128, 9, 1160, 1)
 SOT_DECLARE_CONFIG(128, 17, 2184, 2)
 SOT_DECLARE_CONFIG(256, 17, 4360, 2)
 SOT_DECLARE_CONFIG(256, 33, 8456, 1)
+#ifdef SOT_TUNING_CONFIGS
+SOT_DECLARE_CONFIG(32, 9, 296, 2)
+SOT_DECLARE_CONFIG(64, 17, 1032, 2)
+SOT_DECLARE_CONFIG(128, 9, 1032, 1)
+SOT_DECLARE_CONFIG(32, 33, 1064, 2)
+SOT_DECLARE_CONFIG(32, 33, 1064, 1)
+#endif
 
 namespace sot {
 // ------------------------------------------------------------------------------------------
 // grad rows scaled by a per-frame factor: out[r, :] = unit[r, :] * s[r]   (backward of the
 // "fused" mode, where the forward launch already produced d loss_r / d input)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sot_scale_rows_kernel(const float* __restrict__ unit,
-                                                             const float* __restrict__ s,
-                                                             float* __restrict__ out, long long rows, int width) {
-    const long long total = rows * width;
+// One warp per row (grid-stride over rows): the factor is read once per row, no per-element division; `out`
+// may alias `unit`.
+__global__ void __launch_bounds__(256) sot_scale_rows_kernel(const float* unit, const float* __restrict__ s,
+                                                             float* out, long long rows, int width) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+        const float f = s[r];
+        const float* src = unit + r * width;
+        float* dst = out + r * width;
+        for (int c = lane; c < width; c += 32) dst[c] = src[c] * f;
+    }
+}
+
+// rows *= *scale, in place, for up to two buffers -- the whole backward of a step whose forward launch already
+// produced the gradients of the mean (`sot_mean_step_device`).  The usual upstream gradient of a loss is exactly
+// 1 (trainer.py:220,233-238: weight 1, `.mean()` of a scalar): every thread reads the scalar and leaves.
+__global__ void __launch_bounds__(256) sot_scale_inplace_kernel(float* a, long long na, float* b, long long nb,
+                                                                const float* __restrict__ scale) {
+    const float f = *scale;
+    if (f == 1.0f) return;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += stride) {
-        out[idx] = unit[idx] * s[idx / width];
+    for (int which = 0; which < 2; ++which) {
+        float* p = which == 0 ? a : b;
+        const long long n = which == 0 ? na : nb;
+        if (p == nullptr || n <= 0) continue;
+        // scalar head up to the first 16-byte boundary, float4 body, scalar tail
+        const long long head = min(n, static_cast<long long>((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) >> 2);
+        const long long body = (n - head) >> 2;
+        float4* p4 = reinterpret_cast<float4*>(p + head);
+        for (long long i = tid; i < body; i += stride) {
+            float4 x = p4[i];
+            x.x *= f;
+            x.y *= f;
+            x.z *= f;
+            x.w *= f;
+            p4[i] = x;
+        }
+        const long long done = head + 4 * body;
+        if (tid < head) p[tid] *= f;
+        if (tid < n - done) p[done + tid] *= f;
     }
 }
 
@@ -82,14 +120,16 @@ struct Config {
 // (choices from measurements on B200, profiles/).  Shared memory per CTA = (4 or 6) * 4 * rs bytes.
 const Config kConfigs[] = {
     {32, 9, 296, 1, sot_launch_32_9_296_1},      // <= 288 bins   (n_fft 512: 257)
-    {32, 9, 296, 2, sot_launch_32_9_296_2},      //               (two-chain variant, tuning only: measured slower)
     {64, 9, 584, 2, sot_launch_64_9_584_2},      // <= 576 bins   (n_fft 1024: 513)
     {64, 17, 1032, 1, sot_launch_64_17_1032_1},  // <= 1025 bins  (n_fft 2048: 1025) -- measured best of the five
-    {64, 17, 1032, 2, sot_launch_64_17_1032_2},  //               (tuning alternatives for 1025)
+#ifdef SOT_TUNING_CONFIGS
+    {32, 9, 296, 2, sot_launch_32_9_296_2},      // two-chain variant: measured slower
+    {64, 17, 1032, 2, sot_launch_64_17_1032_2},  // alternatives for 1025 bins (profiles/r01j_tuning_experiments.txt)
     {128, 9, 1032, 1, sot_launch_128_9_1032_1},
     {32, 33, 1064, 2, sot_launch_32_33_1064_2},
-    {32, 33, 1064, 1, sot_launch_32_33_1064_1},  // one warp per frame, one chain (tuning only: the loss-only kernel is
-                                                 // 8 % faster than 64 x 17, the gradient kernel 20 % slower -- 168 registers)
+    {32, 33, 1064, 1, sot_launch_32_33_1064_1},  // one warp per frame, one chain: the loss-only kernel is 8 % faster
+                                                 // than 64 x 17, the gradient kernel 20 % slower -- 168 registers
+#endif
     {128, 9, 1160, 1, sot_launch_128_9_1160_1},    // <= 1152 bins
     {128, 17, 2184, 2, sot_launch_128_17_2184_2},  // <= 2176 bins  (n_fft 4096: 2049)
     {256, 17, 4360, 2, sot_launch_256_17_4360_2},  // <= 4352 bins  (n_fft 8192: 4097)
@@ -161,6 +201,7 @@ sot::FrameArgs base_args(const sot_problem* p) {
     a.flags = p->flags;
     a.one = a.one_b = 1.0f;
     a.neg_zero = a.neg_zero_b = -0.0f;
+    a.upstream_value = 1.0f;
     return a;
 }
 
@@ -280,15 +321,65 @@ int sot_scale_rows_device(const float* unit, const float* scale, float* out, int
     if (rows < 0 || width < 1) return fail(SOT_EINVAL, "bad sizes: rows=%lld width=%d", (long long)rows, width);
     if (rows == 0) return SOT_OK;
     if (unit == nullptr || scale == nullptr || out == nullptr) return fail(SOT_EINVAL, "NULL pointer");
-    const long long total = rows * width;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    long long blocks = (rows + 7) / 8;  // one warp per row, eight rows per block
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
     sot::sot_scale_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         unit, scale, out, rows, width);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "sot_scale_rows_kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return SOT_OK;
+}
+
+int sot_scale_inplace_device(float* rows_a, int64_t count_a, float* rows_b, int64_t count_b, const float* scale,
+                             void* stream) {
+    if (count_a < 0 || count_b < 0) return fail(SOT_EINVAL, "bad sizes: count_a=%lld count_b=%lld", (long long)count_a,
+                                                (long long)count_b);
+    if (scale == nullptr) return fail(SOT_EINVAL, "scale is NULL");
+    if ((rows_a == nullptr || count_a == 0) && (rows_b == nullptr || count_b == 0)) return SOT_OK;
+    const long long most = count_a > count_b ? count_a : count_b;
+    long long blocks = (most / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    sot::sot_scale_inplace_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        rows_a, rows_a != nullptr ? count_a : 0, rows_b, rows_b != nullptr ? count_b : 0, scale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "sot_scale_inplace_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SOT_OK;
+}
+
+int sot_mean_step_device(const sot_problem* prob, const sot_mean_plan* plan, float* loss, float* grad_u, float* grad_v,
+                         void* stream) {
+    if (int rc = validate(prob)) return rc;
+    if (plan == nullptr || plan->workspace == nullptr) return fail(SOT_EINVAL, "plan or plan->workspace is NULL");
+    if (plan->post_world < 0 || plan->post_world > 16 || (plan->post_world > 0 && plan->post_mailboxes == nullptr) ||
+        (plan->post_world > 0 && (plan->post_rank < 0 || plan->post_rank >= plan->post_world ||
+                                  (plan->post_seq == 0 && plan->post_seq_device == nullptr))))
+        return fail(SOT_EINVAL, "bad peer-mailbox description in the plan");
+    if (prob->n_frames == 0) return fail(SOT_EINVAL, "sot_mean_step_device needs at least one frame");
+    const bool grads = grad_u != nullptr || grad_v != nullptr;
+    sot::LaunchRequest r{base_args(prob), grads ? sot::OUT_GRAD : sot::OUT_LOSS, sot::MODE_SPECTRA};
+    r.args.loss = loss;
+    r.args.grad_u = grad_u;
+    r.args.grad_v = grad_v;
+    r.args.upstream_value = plan->grad_scale;
+    r.args.upstream_scale = plan->grad_scale_device;
+    r.args.loss_sum = plan->workspace;
+    r.args.ticket = reinterpret_cast<unsigned int*>(plan->workspace + 1);
+    r.args.mean_out = plan->mean_out;
+    r.args.mean_scale = plan->mean_scale;
+    r.args.total_out = plan->total_out;
+    r.args.post_count = plan->count_value;
+    r.args.post_world = plan->post_world;
+    r.args.post_rank = plan->post_rank;
+    r.args.post_seq = plan->post_seq;
+    r.args.post_seq_dev = reinterpret_cast<unsigned long long*>(plan->post_seq_device);
+    for (int k = 0; k < plan->post_world; ++k) {
+        if (plan->post_mailboxes[k] == nullptr) return fail(SOT_EINVAL, "NULL peer mailbox");
+        r.args.post_mailbox[k] = static_cast<double*>(plan->post_mailboxes[k]);
+    }
+    return launch(prob, r, stream);
 }
 
 int sot_quantile_lookup_device(const float* qs, const float* cws, const float* xs, float* out, int64_t rows,
@@ -365,11 +456,14 @@ struct HostWorkspace {
     bool ready = false;
     size_t cap_dpu = 0, cap_dpv = 0;
     float *d_pu = nullptr, *d_pv = nullptr;
+    // content of the shared support rows that are on the device already (re-sent only when they change)
+    float *h_pu = nullptr, *h_pv = nullptr;
+    size_t len_pu = 0, len_pv = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     HostSlot slot[kSlots];
 };
 HostWorkspace g_ws[kMaxDevices];
-std::mutex g_ws_mutex;
+std::mutex g_ws_mutex[kMaxDevices];  // one per device: ranks / threads driving different GPUs do not serialise
 
 cudaError_t grow(float** p, size_t* cap, size_t bytes) {
     if (bytes <= *cap) return cudaSuccess;
@@ -382,6 +476,20 @@ cudaError_t grow(float** p, size_t* cap, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes);
     if (e == cudaSuccess) *cap = bytes;
     return e;
+}
+
+// shared support row -> device, unless the same values are there already
+cudaError_t sync_positions(float** dev, size_t* cap, float** shadow, size_t* len, const float* host, size_t n,
+                           cudaStream_t stream) {
+    if (*dev != nullptr && *shadow != nullptr && *len == n && memcmp(*shadow, host, 4 * n) == 0) return cudaSuccess;
+    cudaError_t e = grow(dev, cap, 4 * n);
+    if (e != cudaSuccess) return e;
+    float* copy = static_cast<float*>(realloc(*shadow, 4 * n));
+    if (copy == nullptr) return cudaErrorMemoryAllocation;
+    memcpy(copy, host, 4 * n);
+    *shadow = copy;
+    *len = n;
+    return cudaMemcpyAsync(*dev, copy, 4 * n, cudaMemcpyHostToDevice, stream);
 }
 
 void release(HostWorkspace& w) {
@@ -401,6 +509,8 @@ void release(HostWorkspace& w) {
     }
     cudaFree(w.d_pu);
     cudaFree(w.d_pv);
+    free(w.h_pu);
+    free(w.h_pv);
     if (w.s_in) cudaStreamDestroy(w.s_in);
     if (w.s_k) cudaStreamDestroy(w.s_k);
     if (w.s_out) cudaStreamDestroy(w.s_out);
@@ -413,7 +523,7 @@ extern "C" {
 
 int sot_host_release(int32_t device) {
     if (device < 0 || device >= kMaxDevices) return fail(SOT_EINVAL, "bad device ordinal %d", device);
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    std::lock_guard<std::mutex> lock(g_ws_mutex[device]);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     release(g_ws[device]);
@@ -424,7 +534,10 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
                        int32_t device) {
     if (int rc = validate(hp)) return rc;
     if (device < 0 || device >= kMaxDevices) return fail(SOT_EINVAL, "bad device ordinal %d", device);
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    // the staging buffers, copies and host offsets below are sized for real rows (4 bytes per bin)
+    if (hp->flags & SOT_COMPLEX_INPUT)
+        return fail(SOT_EINVAL, "SOT_COMPLEX_INPUT is not supported by the host-buffer entry point (device entries only)");
+    std::lock_guard<std::mutex> lock(g_ws_mutex[device]);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     const long long N = hp->n_frames;
@@ -470,14 +583,8 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
             }
             w.ready = true;
         }
-        if (su) {
-            SOT_CK(grow(&w.d_pu, &w.cap_dpu, 4ULL * n));
-            SOT_CK(cudaMemcpyAsync(w.d_pu, hp->pos_u, 4ULL * n, cudaMemcpyHostToDevice, w.s_in));
-        }
-        if (sv) {
-            SOT_CK(grow(&w.d_pv, &w.cap_dpv, 4ULL * m));
-            SOT_CK(cudaMemcpyAsync(w.d_pv, hp->pos_v, 4ULL * m, cudaMemcpyHostToDevice, w.s_in));
-        }
+        if (su) SOT_CK(sync_positions(&w.d_pu, &w.cap_dpu, &w.h_pu, &w.len_pu, hp->pos_u, n, w.s_in));
+        if (sv) SOT_CK(sync_positions(&w.d_pv, &w.cap_dpv, &w.h_pv, &w.len_pv, hp->pos_v, m, w.s_in));
         for (int k = 0; k < kSlots; ++k) {
             HostSlot& s = w.slot[k];
             SOT_CK(grow(&s.u, &s.cap_u, 4ULL * chunk * n));

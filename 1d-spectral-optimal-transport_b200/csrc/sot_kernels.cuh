@@ -80,8 +80,26 @@ struct FrameArgs {
     long long pos_v_stride;
     const float* upstream;        // [n_frames] dL_total/dloss_n, or nullptr (= 1)
     const float* upstream_scale;  // device scalar multiplying every upstream value, or nullptr (= 1)
+    float upstream_value;         // host constant multiplying every upstream value (1 when unused)
     float* loss;                  // [n_frames] or nullptr
     double* loss_sum;             // device scalar: += sum of the per-frame losses of this launch, or nullptr
+    // Mean of the launch finished by its LAST CTA (the reference's closing `torch.mean`, losses.py:211, without
+    // a memset, a division or a cast kernel around the launch).  `ticket` (nullable; zero before the launch)
+    // counts the CTAs that have added their part to *loss_sum; the last one reads the total, writes
+    //   *mean_out = (float)(total * mean_scale)          (nullable)
+    //   total_out[0] = total, total_out[1] = post_count  (nullable; what an NCCL all-reduce of the shards sums)
+    //   (total, post_count, post_seq) into the mailbox of every peer (post_world > 0; layout of sot_p2p.cu)
+    // and leaves *loss_sum = 0, *ticket = 0 for the next launch on the same workspace.
+    unsigned int* ticket;
+    float* mean_out;
+    double mean_scale;
+    double* total_out;
+    double post_count;
+    double* post_mailbox[16];
+    int post_world, post_rank;
+    unsigned long long post_seq;
+    unsigned long long* post_seq_dev;  // nullable: the sequence number lives on the device (*post_seq_dev + 1, stored
+                                       // back), so that a CUDA graph holding this launch can be replayed
     // "saved merge indices": the merge-path co-rank (number of u entries before the chunk) of every
     // chunk of every frame, [n_frames, NCH * TPF] uint16.  The forward launch can save them, the backward
     // launch of the same configuration can reuse them instead of searching again (both nullable).
@@ -471,6 +489,42 @@ SOT_DEVINL bool row_is_bulk(const float* base, long long f, int width, long long
 
 template <int N>
 using IC = std::integral_constant<int, N>;
+
+// Called by one thread per CTA after its atomicAdd into *loss_sum: the CTA that draws the last ticket owns the
+// total (every other CTA's add is ordered before its ticket by the fence) and finishes the mean -- see FrameArgs.
+// Mailbox layout = sot_p2p.cu: slot [rank][phase = seq & 1] of kP2PSlot = 9 doubles, entry [8] = sequence number.
+SOT_DEVINL void finish_mean(const FrameArgs& args) {
+    __threadfence();
+    if (atomicAdd(args.ticket, 1u) != gridDim.x - 1) return;
+    __threadfence();
+    const double total = __longlong_as_double(static_cast<long long>(
+        atomicExch(reinterpret_cast<unsigned long long*>(args.loss_sum), 0ULL)));
+    *args.ticket = 0;
+    if (args.mean_out != nullptr) *args.mean_out = static_cast<float>(total * args.mean_scale);
+    if (args.total_out != nullptr) {
+        args.total_out[0] = total;
+        args.total_out[1] = args.post_count;
+    }
+    if (args.post_world > 0) {
+        unsigned long long seq = args.post_seq;
+        if (args.post_seq_dev != nullptr) {
+            seq = *args.post_seq_dev + 1ULL;
+            *args.post_seq_dev = seq;
+        }
+        const int phase = static_cast<int>(seq & 1ULL);
+        for (int r = 0; r < args.post_world; ++r) {
+            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 2 + phase) * 9;
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(total) : "memory");
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + 1), "d"(args.post_count) : "memory");
+        }
+        __threadfence_system();
+        const double seq_val = static_cast<double>(seq);
+        for (int r = 0; r < args.post_world; ++r) {
+            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 2 + phase) * 9;
+            asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + 8), "d"(seq_val) : "memory");
+        }
+    }
+}
 
 template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int OUT, int MODE>
 __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH, UNI, CPLX>::TOTAL, OUT))
@@ -1118,7 +1172,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 // gw = offset + local suffix; (offset - corr) is formed in fp64 before rounding
                 const float bu = static_cast<float>(off_u - corr_u), bv = static_cast<float>(off_v - corr_v);
                 const float up = (args.upstream != nullptr ? args.upstream[frame] : 1.0f) *
-                                 (args.upstream_scale != nullptr ? *args.upstream_scale : 1.0f);
+                                 (args.upstream_scale != nullptr ? *args.upstream_scale : 1.0f) * args.upstream_value;
                 const float ku = finite ? static_cast<float>(inv_u) * up * (square ? 2.0f : 1.0f) : f_nan();
                 const float kv = finite ? static_cast<float>(inv_v) * up * (square ? 2.0f : 1.0f) : f_nan();
                 if constexpr (!CPLX) {
@@ -1221,7 +1275,10 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             }
         }
     }
-    if (tid == 0 && args.loss_sum != nullptr) atomicAdd(args.loss_sum, cta_loss);  // one atomic per CTA
+    if (tid == 0 && args.loss_sum != nullptr) {
+        atomicAdd(args.loss_sum, cta_loss);  // one atomic per CTA
+        if (args.ticket != nullptr) finish_mean(args);
+    }
     if constexpr (WITH_GRAD) {
         if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store
     }

@@ -3,6 +3,8 @@
 //   TPF threads per frame (= per CTA), E (odd) consecutive bins per thread, RS floats per
 //   shared-memory row; the configuration accepts rows of up to min(TPF * E, RS - 7) bins.
 #pragma once
+#include <atomic>
+
 #include "sot_kernels.cuh"
 
 namespace sot {
@@ -17,12 +19,17 @@ template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int O
 cudaError_t launch_one(const FrameArgs& a, cudaStream_t stream) {
     auto kernel = sot_frame_kernel<TPF, E, RS, NCH, UNI, CPLX, PMODE, OUT, MODE>;
     constexpr int smem_bytes = static_cast<int>(Layout<TPF, RS, OUT, NCH, UNI, CPLX>::TOTAL);
-    // per instantiation (and device): opt-in shared memory size and the persistent grid size
-    static int cached_grid = 0, cached_dev = -1;
+    // per instantiation AND device: opt-in shared memory size and the persistent grid size.  The forward is launched
+    // from the caller's thread, the backward from the autograd engine's thread of that device, and one process may
+    // drive several devices: one atomic slot per device ordinal, 0 = not set up yet.  Two threads that both see 0
+    // both run the (idempotent) set-up and store the same value.
+    constexpr int kMaxDev = 64;
+    static std::atomic<int> grid_of_dev[kMaxDev];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev != cached_dev) {
+    int cached_grid = (dev >= 0 && dev < kMaxDev) ? grid_of_dev[dev].load(std::memory_order_acquire) : 0;
+    if (cached_grid == 0) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return e;
         int per_sm = 0, sms = 0;
@@ -31,7 +38,7 @@ cudaError_t launch_one(const FrameArgs& a, cudaStream_t stream) {
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         cached_grid = (per_sm < 1 ? 1 : per_sm) * sms;  // persistent: every CTA slot of the chip, once
-        cached_dev = dev;
+        if (dev >= 0 && dev < kMaxDev) grid_of_dev[dev].store(cached_grid, std::memory_order_release);
     }
     const unsigned grid = static_cast<unsigned>(a.n_frames < cached_grid ? a.n_frames : cached_grid);
     kernel<<<grid, TPF, smem_bytes, stream>>>(a);

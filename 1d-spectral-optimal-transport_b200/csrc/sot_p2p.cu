@@ -4,6 +4,9 @@
 // stores into every peer's mailbox and spins on its own costs a few microseconds where an NCCL all-reduce
 // (launch + protocol) costs tens.
 //
+// The stores can also be made by the SOT launch itself (its last CTA, `finish_mean` in sot_kernels.cuh: the compute
+// kernel starts the exchange the moment its sum is complete) and collected by the wait-only form of this kernel.
+//
 // Mailbox (one per rank, symmetric allocation, peers mapped): [world][2 phases][kMaxVals + 1] doubles; entry
 // [r][ph][kMaxVals] is the sequence number rank r wrote last into phase ph.  Call number `seq` (1, 2, ...) uses
 // phase seq & 1: a rank can only start call seq + 2 (same phase) after every peer has written call seq + 1, i.e.
@@ -11,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/sot_b200.h"
 
@@ -32,6 +36,12 @@ struct P2PArgs {
     int count, world, rank;
     unsigned long long seq;
     unsigned long long timeout_ns;
+    // wait-only form: the stores into the peers' mailboxes were made by the last CTA of the SOT launch
+    // (sot_kernels.cuh: finish_mean); this kernel only collects.  expected_count > 0: the counts must add up to it.
+    int post;
+    unsigned long long* seq_dev;  // nullable: call number = *seq_dev + 1, stored back at the end (graph replay)
+    double expected_count;
+    int* status;  // nullable: 1 = count mismatch, 2 = a peer never arrived
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -42,20 +52,23 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) {
     const int t = threadIdx.x;
-    const int phase = static_cast<int>(a.seq & 1ULL);
-    const double seq_val = static_cast<double>(a.seq);
+    const unsigned long long seq = a.seq_dev != nullptr ? *a.seq_dev + 1ULL : a.seq;
+    const int phase = static_cast<int>(seq & 1ULL);
+    const double seq_val = static_cast<double>(seq);
     __shared__ int failed;
     if (t == 0) failed = 0;
     __syncwarp();
     if (t < a.world) {
-        // my values, then my sequence number, into slot [rank][phase] of peer t's mailbox
-        double* dst = a.mailbox[t] + (static_cast<long long>(a.rank) * 2 + phase) * kP2PSlot;
-        for (int i = 0; i < a.count; ++i) {
-            const double v = (a.mean_out != nullptr && i == 1) ? a.local_count : a.in[i];
-            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + i), "d"(v) : "memory");
+        if (a.post) {
+            // my values, then my sequence number, into slot [rank][phase] of peer t's mailbox
+            double* dst = a.mailbox[t] + (static_cast<long long>(a.rank) * 2 + phase) * kP2PSlot;
+            for (int i = 0; i < a.count; ++i) {
+                const double v = (a.mean_out != nullptr && i == 1) ? a.local_count : a.in[i];
+                asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + i), "d"(v) : "memory");
+            }
+            __threadfence_system();
+            asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + kP2PMaxVals), "d"(seq_val) : "memory");
         }
-        __threadfence_system();
-        asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + kP2PMaxVals), "d"(seq_val) : "memory");
         // wait for rank t's contribution in my own mailbox
         const double* src = a.mailbox[a.rank] + (static_cast<long long>(t) * 2 + phase) * kP2PSlot;
         const unsigned long long t0 = global_ns();
@@ -63,12 +76,23 @@ __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) 
         do {
             asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(seen) : "l"(src + kP2PMaxVals) : "memory");
             if (seen != seq_val && global_ns() - t0 > a.timeout_ns) {
-                failed = 1;  // a peer never arrived: poison the result instead of hanging the GPU
+                failed = 1;
                 break;
             }
         } while (seen != seq_val);
     }
     __syncwarp();
+    if (failed) {
+        // A peer never arrived (timeout on NCCL's watchdog scale, minutes): fail LOUDLY -- the status word is
+        // set for the host and the kernel traps, so the next CUDA call on this context returns an error
+        // (a silent NaN would be all-reduced into every replica's weights by DDP).
+        if (t == 0 && a.status != nullptr) {
+            *a.status = 2;
+            __threadfence_system();
+        }
+        __syncwarp();
+        __trap();
+    }
     if (t < a.count) {
         double s = 0.0;
         for (int r = 0; r < a.world; ++r) {  // fixed order: every rank gets the same bits
@@ -79,13 +103,15 @@ __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) 
                          : "memory");
             s += v;
         }
-        s = failed ? __longlong_as_double(0x7ff8000000000000LL) : s;
+        if (a.seq_dev != nullptr && t == 0) *a.seq_dev = seq;  // (every lane read the old value before the spin)
         if (a.out != nullptr) a.out[t] = s;
         if (a.mean_out != nullptr) {  // t = 0 holds the sum, t = 1 the count
             const double cnt = __shfl_sync((1u << a.count) - 1u, s, 1);
             if (t == 0) {
-                *a.mean_out = static_cast<float>(s / cnt);
-                *a.inv_count_out = static_cast<float>(1.0 / cnt);
+                const bool count_ok = !(a.expected_count > 0.0) || cnt == a.expected_count;
+                *a.mean_out = count_ok ? static_cast<float>(s / cnt) : __int_as_float(0x7fc00000);
+                if (a.inv_count_out != nullptr) *a.inv_count_out = static_cast<float>(1.0 / cnt);
+                if (!count_ok && a.status != nullptr) *a.status = 1;
             }
         }
     }
@@ -112,6 +138,24 @@ int sot_p2p_global_mean_device(const double* local_sum, double local_count, floa
     a.mean_out = mean_out;
     a.inv_count_out = inv_count_out;
     a.count = 2;
+    a.post = 1;
+    return p2p_launch(a, mailboxes, world, rank, seq, stream);
+}
+
+int sot_p2p_wait_mean_device(float* mean_out, double expected_count, int32_t* status, void* const* mailboxes,
+                             int32_t world, int32_t rank, uint64_t seq, uint64_t* seq_device, uint32_t timeout_ms,
+                             void* stream) {
+    if (mean_out == nullptr || mailboxes == nullptr)
+        return sot_mss_fail(SOT_EINVAL, "sot_p2p_wait_mean_device: NULL pointer");
+    sot::P2PArgs a{};
+    a.mean_out = mean_out;
+    a.count = 2;
+    a.post = 0;
+    a.expected_count = expected_count;
+    a.status = status;
+    a.seq_dev = reinterpret_cast<unsigned long long*>(seq_device);
+    if (seq_device != nullptr && seq == 0) seq = 1;  // (argument check below; the device value is what counts)
+    if (timeout_ms > 0) a.timeout_ns = 1000000ULL * timeout_ms;
     return p2p_launch(a, mailboxes, world, rank, seq, stream);
 }
 
@@ -125,6 +169,7 @@ int sot_p2p_allreduce_device(const double* in, double* out, int32_t count, void*
     a.in = in;
     a.out = out;
     a.count = count;
+    a.post = 1;
     return p2p_launch(a, mailboxes, world, rank, seq, stream);
 }
 
@@ -140,7 +185,14 @@ static int p2p_launch(sot::P2PArgs& a, void* const* mailboxes, int32_t world, in
     a.world = world;
     a.rank = rank;
     a.seq = seq;
-    a.timeout_ns = 2000000000ULL;  // 2 s
+    if (a.timeout_ns == 0) {  // a late peer is normal (checkpointing, evaluation, a data-loader stall on one rank):
+        unsigned long long ms = 600000ULL;  // wait on NCCL's watchdog scale, 10 minutes, unless told otherwise
+        if (const char* env = getenv("SOT_P2P_TIMEOUT_MS")) {
+            const long long v = atoll(env);
+            if (v > 0) ms = static_cast<unsigned long long>(v);
+        }
+        a.timeout_ns = 1000000ULL * ms;
+    }
     sot::sot_p2p_allreduce_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return sot_mss_fail(static_cast<int>(e), cudaGetErrorString(e));

@@ -19,8 +19,9 @@ from . import _capi
 
 __all__ = ["Wasserstein1D", "wasserstein_1d", "quantile_function", "sot_frames", "sot_mean"]
 
-BACKWARD_MODES = ("recompute", "fused")
-_LOCAL_ONLY = object()  # sentinel "process group": never reduce across ranks
+BACKWARD_MODES = ("recompute", "fused")       # per-frame values (`sot_frames`: hinge, `dims`, `wasserstein_1d`)
+MEAN_BACKWARD_MODES = ("onepass", "recompute")  # the plain mean over all frames (every paper config)
+DEFAULT_BACKWARD_MODE = "onepass"
 
 
 # --------------------------------------------------------------------------------------
@@ -231,63 +232,61 @@ def sot_frames(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=Fal
 class _SotMean(torch.autograd.Function):
     """rows (N, n), (N, m) -> mean over the frames of ALL ranks of W_p^p, a 0-dim tensor.
 
-    The mean the reference takes at the end (losses.py:211) folded into the two launches: the forward
-    kernel accumulates the sum of the per-frame losses on the device (one fp64 atomic per CTA), the
-    backward kernel reads dL/dmean / N from a device scalar.  No reduction kernel, no per-frame
-    upstream vector, no host synchronisation.  With a process group the only collective is one
-    all-reduce of (sum, count)."""
+    The mean the reference takes at the end (losses.py:211) and the whole backward folded into ONE launch
+    (mode "onepass"): when a gradient is required the forward launches the fused forward+backward kernel, which
+    writes the gradient rows of the mean (already scaled by 1/N_global) and whose last CTA writes the float mean --
+    no memset, division, cast or reduction kernel, no host synchronisation.  The backward is an in-place
+    `rows *= dL/dmean` that leaves at once when the upstream gradient is exactly 1 (trainer.py:220,233-238: the
+    loss enters the total with weight 1).  Mode "recompute" keeps nothing between the passes: loss-only launch
+    forward, fused launch backward.  With an `exchange` (sharding.MeanExchange) the per-rank sums meet in ONE
+    exchange that the backward never waits for: 1/N_global depends on the frame counts only."""
 
     @staticmethod
-    def forward(ctx, u, v, pos_u, pos_v, p, flags, group):
-        import torch.distributed as dist
-        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        total, _, coranks = _capi.forward_sum(u, v, pos_u, pos_v, p, flags, save_coranks=need_grad)
-        ctx.coranks = coranks  # merge indices saved for the backward launch (not a differentiable input)
-        count = float(u.shape[0])
-        ctx.p, ctx.flags = p, flags
-        ctx.need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        peer = hasattr(group, "all_reduce") and hasattr(group, "world")  # sharding.PeerReducer (NVLink mailboxes)
-        if group is not _LOCAL_ONLY and dist.is_available() and dist.is_initialized() and \
-                (group.world if peer else dist.get_world_size(group)) > 1:
-            if peer:  # one kernel: exchange over NVLink, mean and 1/count come back as floats
-                mean, inv_count = group.global_mean(total, count)
-                ctx.count = None
-                ctx.inv_count = True
-                ctx.save_for_backward(u, v, pos_u, pos_v, inv_count)
-                return mean[0]
-            ctx.inv_count = False
-            stats = torch.cat((total, torch.full_like(total, count)))
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
-            ctx.count = None
-            ctx.save_for_backward(u, v, pos_u, pos_v, stats[1:2])
-            return (stats[0] / stats[1]).to(torch.float32)
-        ctx.count = count
-        ctx.save_for_backward(u, v, pos_u, pos_v)
-        return (total[0] / count).to(torch.float32)
+    def forward(ctx, u, v, pos_u, pos_v, p, flags, exchange, mode):
+        need_u, need_v = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        n_local = u.shape[0]
+        kw = {}
+        n_global = float(n_local)
+        if exchange is not None:
+            n_global = exchange.global_count(n_local, u.device)
+            kw = exchange.launch_kwargs(n_local, u.device)
+        onepass = mode == "onepass" and (need_u or need_v)
+        mean, _, gu, gv = _capi.mean_step(u, v, pos_u, pos_v, p, flags, grad_scale=1.0 / n_global,
+                                          mean_scale=1.0 / n_local, want_gu=onepass and need_u,
+                                          want_gv=onepass and need_v, **kw)
+        if exchange is not None:
+            mean = exchange.finish(kw, n_global, u.device)
+        ctx.p, ctx.flags, ctx.need, ctx.n_global = p, flags, (need_u, need_v), n_global
+        ctx.gu, ctx.gv = gu, gv  # taken (and dropped) by the first backward
+        ctx.save_for_backward(u, v, pos_u, pos_v)  # references only; a repeated backward recomputes from them
+        return mean
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        if ctx.count is None and ctx.inv_count:
-            u, v, pos_u, pos_v, inv_count = ctx.saved_tensors
-            scale = (grad_out.to(torch.float32) * inv_count).reshape(1)
-        elif ctx.count is None:
-            u, v, pos_u, pos_v, count = ctx.saved_tensors
-            scale = (grad_out.to(torch.float64) / count).to(torch.float32).reshape(1)
-        else:
+        need_u, need_v = ctx.need
+        g = grad_out.detach().to(torch.float32).reshape(1)
+        gu, gv = ctx.gu, ctx.gv
+        ctx.gu = ctx.gv = None
+        if gu is not None or gv is not None:
+            _capi.scale_inplace(gu, gv, g)  # leaves at once for an upstream gradient of exactly 1
+        else:  # "recompute" mode, or a second backward through a retained graph
             u, v, pos_u, pos_v = ctx.saved_tensors
-            scale = (grad_out / ctx.count).to(torch.float32).reshape(1)
-        gu, gv = _capi.forward_backward_scaled(u, v, pos_u, pos_v, ctx.p, ctx.flags, scale.contiguous(),
-                                               ctx.coranks, ctx.need[0], ctx.need[1])
-        return gu, gv, None, None, None, None, None
+            _, _, gu, gv = _capi.mean_step(u, v, pos_u, pos_v, ctx.p, ctx.flags, grad_scale=1.0 / ctx.n_global,
+                                           mean_scale=0.0, want_gu=need_u, want_gv=need_v, grad_scale_device=g,
+                                           want_mean=False)
+        return gu, gv, None, None, None, None, None, None
 
 
 def sot_mean(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=False, require_sort=True,
-             raw_weights=False, group=None) -> torch.Tensor:
-    """mean_n W_p^p(frame n) over this rank's frames -- and over all ranks' when `group` (or the default
-    process group) spans more than one -- differentiable w.r.t. x and y.  Two kernel launches a step."""
+             raw_weights=False, exchange=None, backward_mode="onepass") -> torch.Tensor:
+    """mean_n W_p^p(frame n) over this rank's frames -- and over all ranks' when `exchange` (a
+    `sharding.MeanExchange`) spans more than one -- differentiable w.r.t. x and y.  One SOT launch a step plus the
+    in-place scaling of the backward."""
+    if backward_mode not in MEAN_BACKWARD_MODES:
+        raise ValueError(f"backward_mode must be one of {MEAN_BACKWARD_MODES}")
     u, v, pu, pv, flags = _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights)
-    return _SotMean.apply(u, v, pu, pv, float(p), flags, group)
+    return _SotMean.apply(u, v, pu, pv, float(p), flags, exchange, backward_mode)
 
 
 # --------------------------------------------------------------------------------------
@@ -296,8 +295,11 @@ def sot_mean(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=False
 class Wasserstein1D(torch.nn.Module):
     def __init__(self, p=1, fixed_x=None, require_sort=True, log_scaled_x=False, **kwargs):
         """Same arguments as the reference (losses.py:90-127).  `kwargs` read: dont_normalize,
-        limit_quantile_range, hinge, square_dist -- plus `backward_mode` ("recompute" | "fused"),
-        which only this implementation knows; any other key is ignored like the reference does."""
+        limit_quantile_range, hinge, square_dist -- plus `backward_mode`, which only this implementation knows:
+        "onepass" (default: ONE fused launch per step, gradients produced by the forward launch), "recompute"
+        (nothing kept between the passes: loss-only launch forward, fused launch backward) or "fused" (alias of
+        "onepass" for the mean; per-frame outputs: unit gradients saved, row scaling backward).  Any other key is
+        ignored like the reference does."""
         super().__init__()
         self.p = p
         self.require_sort = require_sort
@@ -306,16 +308,18 @@ class Wasserstein1D(torch.nn.Module):
         self.limit_quantile_range = kwargs.get("limit_quantile_range", False)
         self.hinge = kwargs.get("hinge", False)
         self.square_dist = kwargs.get("square_dist", False)
-        self.backward_mode = kwargs.get("backward_mode", "recompute")
+        self.backward_mode = kwargs.get("backward_mode", DEFAULT_BACKWARD_MODE)
+        if self.backward_mode not in ("onepass", "recompute", "fused"):
+            raise ValueError('backward_mode must be "onepass", "recompute" or "fused"')
         if fixed_x is not None:
             self.register_buffer("fixed_x", torch.linspace(0, 1, fixed_x))
         else:
             self.register_buffer("fixed_x", None)
 
-    def _mean_group(self):
-        """Process group whose ranks share the final mean; the single-process reference has none.
+    def _mean_exchange(self):
+        """How the ranks' sums meet for the final mean; the single-process reference has no ranks (None).
         `sharding.ShardedWasserstein1D` overrides this."""
-        return _LOCAL_ONLY
+        return None
 
     def forward(self, x, y, x_pos=None, y_pos=None, **kwargs):
         if (x_pos is None or y_pos is None) and self.fixed_x is None:
@@ -337,13 +341,15 @@ class Wasserstein1D(torch.nn.Module):
             out = _quantiles(x, y, x_pos_, y_pos_, bool(self.square_dist), cut_scale, need_sort)
             return [t.reshape(original_shape + (-1,)) for t in out]  # losses.py:198-201
 
-        mode = getattr(self, "backward_mode", "recompute")
-        if not self.hinge and kwargs.get("dims", None) is None and mode == "recompute" and x.numel() > 0:
-            # plain mean over all frames (every paper config): folded into the two kernel launches
+        mode = getattr(self, "backward_mode", DEFAULT_BACKWARD_MODE)
+        if not self.hinge and kwargs.get("dims", None) is None and x.numel() > 0:
+            # plain mean over all frames (every paper config): folded into the one kernel launch
             return sot_mean(x, y, x_pos_, y_pos_, p=self.p, square=bool(self.square_dist), cut_scale=cut_scale,
-                            limit=limit, require_sort=need_sort, group=self._mean_group())
+                            limit=limit, require_sort=need_sort, exchange=self._mean_exchange(),
+                            backward_mode="recompute" if mode == "recompute" else "onepass")
         loss = sot_frames(x, y, x_pos_, y_pos_, p=self.p, square=bool(self.square_dist), cut_scale=cut_scale,
-                          limit=limit, require_sort=need_sort, backward_mode=mode)
+                          limit=limit, require_sort=need_sort,
+                          backward_mode="recompute" if mode == "recompute" else "fused")
         if self.hinge:  # losses.py:203-205: the ctor flag gates, the call kwarg is the threshold
             loss = torch.nn.functional.relu(loss - kwargs.get("hinge", 0.0))
         loss = loss.reshape(original_shape)

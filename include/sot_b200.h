@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SOT_B200_ABI_VERSION 1
+#define SOT_B200_ABI_VERSION 2
 
 /* flags (bit-or) */
 #define SOT_SQUARE 1    /* square_dist=True: weights = magnitude^2        losses.py:172-174 */
@@ -98,8 +98,45 @@ int sot_forward_backward_scaled_device(const sot_problem* prob, const float* ups
  * bit-identical.  Co-ranks from another kernel configuration (other count) are ignored. */
 int sot_coranks_per_frame(int32_t n_u, int32_t n_v);
 
-/* out[r, :] = unit[r, :] * scale[r]  -- backward of the "fused" autograd mode, where the forward
- * launch already produced the unit gradients. */
+/* ---- the training step in ONE launch ---------------------------------------------------------------
+ * What `loss = Wasserstein1D(...)(x, y, x_pos, y_pos); loss.backward()` needs (trainer.py:209-221, 233-238) is the
+ * mean over the frames (losses.py:211) and its gradient.  `sot_mean_step_device` makes one launch of the fused
+ * forward+backward kernel: gradients come out already scaled by `grad_scale` (1/N for the mean of N frames; 1/N_global
+ * when the frames are sharded over ranks), and the LAST CTA of the launch finishes the mean:
+ *     *mean_out     = (float)(sum_n loss_n * mean_scale)                  (nullable)
+ *     total_out[0]  = sum_n loss_n,  total_out[1] = count_value            (nullable; the two doubles a sharded
+ *                                                                           caller all-reduces with NCCL)
+ *     peer mailboxes: (sum, count_value, post_seq) stored into slot [post_rank] of every rank's mailbox over
+ *                     NVLink (post_world > 0; layout and protocol of sot_p2p_*; `sot_p2p_wait_mean_device`
+ *                     collects them) -- the compute kernel itself starts the one exchange of the sharded loss.
+ * `workspace` = 2 doubles of device memory, zero before the first use; the kernel leaves them zero, so no memset,
+ * division or cast kernels surround the launch.  One workspace per stream that launches concurrently.
+ * grad_u / grad_v nullable (both NULL: the loss-only kernel runs); `loss` (per-frame values) nullable.
+ * The backward of the step is then `sot_scale_inplace_device`: rows *= *scale in place, leaving at once when
+ * *scale == 1 (the upstream gradient of a loss that is summed with weight 1). */
+typedef struct sot_mean_plan {
+    double* workspace;
+    float* mean_out;
+    double mean_scale;
+    double* total_out;
+    double count_value;
+    void* const* post_mailboxes; /* [post_world] device pointers, rank order */
+    int32_t post_world;          /* 0 = no peer exchange */
+    int32_t post_rank;
+    uint64_t post_seq;
+    uint64_t* post_seq_device;   /* nullable; overrides post_seq: the call number is *post_seq_device + 1, stored back
+                                    by the kernel -- a CUDA graph that contains the launch can then be replayed */
+    float grad_scale;
+    const float* grad_scale_device; /* nullable device scalar that also multiplies the gradients (an upstream
+                                       gradient that is only known on the device) */
+} sot_mean_plan;
+int sot_mean_step_device(const sot_problem* prob, const sot_mean_plan* plan, float* loss, float* grad_u,
+                         float* grad_v, void* stream);
+int sot_scale_inplace_device(float* rows_a, int64_t count_a, float* rows_b, int64_t count_b, const float* scale,
+                             void* stream);
+
+/* out[r, :] = unit[r, :] * scale[r]  -- backward of the per-frame "fused" autograd mode, where the forward
+ * launch already produced the unit gradients.  `out` may be `unit`. */
 int sot_scale_rows_device(const float* unit, const float* scale, float* out, int64_t rows,
                           int32_t width, void* stream);
 
@@ -164,7 +201,8 @@ int sot_mss_backward_device(const float* zt, const float* zv, int64_t count, flo
  * NVLink / NVSwitch peer memory, one tiny kernel per call.  `mailboxes[r]` = rank r's mailbox as mapped into this
  * process (a symmetric allocation of sot_p2p_mailbox_doubles(world) doubles per rank, zero-initialised before the
  * first call; e.g. torch.distributed._symmetric_memory), `seq` = 1, 2, 3, ... the same on every rank.  Every rank
- * receives bit-identical sums.  A peer that does not arrive within 2 s poisons the result with NaN (no hang). */
+ * receives bit-identical sums.  A peer that has not arrived after SOT_P2P_TIMEOUT_MS (environment, default 600 000 ms -- NCCL's watchdog scale)
+ * makes the kernel trap: the next CUDA call on the stream fails loudly (never a silent NaN). */
 int sot_p2p_mailbox_doubles(int32_t world);
 /* The form the sharded loss uses: exchanges (*local_sum, local_count) and writes the global mean sum / count and
  * 1 / count as floats (device memory) -- the forward value and the backward's scale, no scalar-sized kernels around
@@ -173,6 +211,15 @@ int sot_p2p_global_mean_device(const double* local_sum, double local_count, floa
                                void* const* mailboxes, int32_t world, int32_t rank, uint64_t seq, void* stream);
 int sot_p2p_allreduce_device(const double* in, double* out, int32_t count, void* const* mailboxes, int32_t world,
                              int32_t rank, uint64_t seq, void* stream);
+/* Second half of an exchange whose first half (the stores into the peers' mailboxes) was done by the last CTA of
+ * `sot_mean_step_device`: waits for call `seq` of every rank in this rank's mailbox, then
+ *     *mean_out = (float)(sum of the sums / sum of the counts);
+ * if the counts do not add up to `expected_count` (> 0) the mean is NaN and *status (nullable; e.g. mapped pinned
+ * host memory) is set to 1; a peer that has not arrived after `timeout_ms` sets *status = 2 and traps. */
+int sot_p2p_wait_mean_device(float* mean_out, double expected_count, int32_t* status, void* const* mailboxes,
+                             int32_t world, int32_t rank, uint64_t seq, uint64_t* seq_device, uint32_t timeout_ms,
+                             void* stream);
+/* (`seq_device` nullable; overrides `seq` like `post_seq_device` above: call number = *seq_device + 1, stored back.) */
 
 /* Tuning override for benchmarking: threads per frame (32/64/128/256), bins per thread (odd) and
  * merge chains per thread (1/2, 0 = any); 0, 0, 0 restores the built-in choice.  Returns SOT_EINVAL

@@ -175,7 +175,10 @@ def test_every_kernel_configuration_takes_complex_rows(capi):
         base = capi.forward_backward(x, y, pos, pos, 2.0, capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT)
         try:
             for tpf, e, nch in tunings:
-                capi.set_tuning(tpf, e, nch)
+                try:
+                    capi.set_tuning(tpf, e, nch)
+                except ValueError:  # an alternative that is only compiled with SOT_BUILD_TUNING=1
+                    continue
                 got = capi.forward_backward(x, y, pos, pos, 2.0, capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT)
                 # (configurations sum different groups of bins locally: CDFs a few ulp apart)
                 assert torch.allclose(got[0], base[0], rtol=1e-5, atol=0), (tpf, e, nch)

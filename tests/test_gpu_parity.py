@@ -8,8 +8,10 @@ Tolerances (float32 arithmetic; stated where used):
   * loss from magnitudes, cutoff mode: the reference is discontinuous in the last ulp of the
     target CDF (strict `qs > 1` mask, App. B) -> compared on the kernel's own CDFs (which must be
     within 4 ulp of the fp64 CDFs) at rel 2e-6, plus aggregate rel 2e-3 vs the reference value.
-  * gradients: rel-L2 vs the fp64 continuation from the same CDFs no worse than
-    max(2e-5, 1.5 x the reference's own fp32 autograd error) per frame.
+  * gradients, two gates: (a) per frame, rel-L2 vs the fp64 continuation of the kernel's own CDFs within
+    4 eps32 x the conditioning number + 2e-6; (b) per fixture and at the paper's batch size, rel-L2 error vs the
+    reference evaluated in float64 (`ref64`: the oracle on upcast inputs) no worse than
+    max(2e-5, 1.5 x the error of the reference's own float32 gradients against the same `ref64`).
 """
 import numpy as np
 import pytest
@@ -36,6 +38,34 @@ def L():
     return losses
 
 
+def _tune(capi, tuning):
+    """Select a kernel configuration; the alternatives of the production choice are only compiled with
+    SOT_BUILD_TUNING=1 (`python -m sot_b200.build`): skip them when absent."""
+    try:
+        _tune(capi, tuning)
+    except ValueError:
+        pytest.skip("kernel configuration not compiled in (build with SOT_BUILD_TUNING=1)")
+
+
+def _rel_l2(a, b):
+    return (torch.linalg.vector_norm(a.double() - b.double()) / torch.linalg.vector_norm(b.double())).item()
+
+
+def _ref64_grads(x, y, px, py, kw, scale=1.0):
+    """Gradients of scale * mean_n loss_n from the reference's formula evaluated in float64 (stable tie order)."""
+    _, gx, gy = O.sot_loss_and_grads(x.double(), y.double(), px.double(), py.double(), stable=True, **kw)
+    return gx * scale, gy * scale
+
+
+def _assert_grad_gate(mine, ref32, ref64, what):
+    """North star: 'loss and gradients within rel 1e-5 in fp32 (tighter against an fp64 reference run)'.  The
+    gradient of this loss is discontinuous in the last ulp of the fp32 CDFs, so the reference's
+    own fp32 gradients sit 1e-4 .. 1e-2 from its fp64 ones; the gate is relative to that."""
+    e_mine, e_ref = _rel_l2(mine, ref64), _rel_l2(ref32, ref64)
+    assert e_mine <= max(2e-5, 1.5 * e_ref), f"{what}: CUDA {e_mine:.3e} vs fp64, reference fp32 {e_ref:.3e} vs fp64"
+    return e_mine, e_ref
+
+
 def _flags(capi, kw):
     return ((capi.SOT_SQUARE if kw["square"] else 0) | (capi.SOT_CUT_SCALE if kw["cut_scale"] else 0) |
             (capi.SOT_LIMIT if kw["limit"] else 0))
@@ -53,7 +83,7 @@ def _sorted_case(g):
 # P1: bit-exact plan from the reference's own CDFs
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", G.MODULE_CASES)
-@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17, 1), (64, 17, 2), (128, 17)])
+@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 9), (64, 17, 1), (64, 17, 2), (128, 9), (128, 17), (256, 17)])
 def test_p1_plan_from_reference_cdfs_bit_exact(capi, name, tuning):
     g = G.load(name)
     F = g["x"].shape[-1]
@@ -61,7 +91,7 @@ def test_p1_plan_from_reference_cdfs_bit_exact(capi, name, tuning):
         pytest.skip("row does not fit this configuration")
     cu, cv = g["cu"].reshape(-1, F).contiguous(), g["cv"].reshape(-1, F).contiguous()
     pos = torch.sort(g["pos_x"], stable=True)[0]
-    capi.set_tuning(*tuning)
+    _tune(capi, tuning)
     try:
         uq, vq, qs, _, _, iu, iv = capi.quantiles(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), 0,
                                                   from_cdf=True, want_indices=True)
@@ -104,7 +134,7 @@ def test_p1_unequal_supports_and_heavy_ties(capi):
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["sot512_cut", "sot512_nocut", "sot2048_cut", "sot2048_nocut", "sot512_logf_cut"])
 @pytest.mark.parametrize("p", [1.0, 2.0, 3.0])
-@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 17, 1), (64, 17, 2), (128, 9)])
+@pytest.mark.parametrize("tuning", [(0, 0), (32, 33), (64, 9), (64, 17, 1), (64, 17, 2), (128, 9), (128, 17)])
 @pytest.mark.parametrize("uniform", [False, True])
 def test_p2_loss_and_cdf_gradients_from_reference_cdfs(capi, name, p, tuning, uniform):
     g = G.load(name)
@@ -117,7 +147,7 @@ def test_p2_loss_and_cdf_gradients_from_reference_cdfs(capi, name, p, tuning, un
     if uniform and g["meta"]["grid"] != "linear":
         pytest.skip("the uniform-grid kernels need an exact linear grid")
     flags = (capi.SOT_LIMIT if limit else 0) | (capi.SOT_UNIFORM_GRID if uniform else 0)
-    capi.set_tuning(*tuning)
+    _tune(capi, tuning)
     try:
         loss, g_cu, g_cv = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p, flags)
         loss_only, _, _ = capi.loss_from_cdf(cu.to(DEV), cv.to(DEV), pos.to(DEV), pos.to(DEV), p, flags,
@@ -172,7 +202,7 @@ def test_kernel_cdfs_within_ulps_of_fp64(capi, L, name):
 
 
 @pytest.mark.parametrize("name", G.MODULE_CASES)
-@pytest.mark.parametrize("mode", ["recompute", "fused"])
+@pytest.mark.parametrize("mode", ["onepass", "recompute"])
 def test_module_forward_backward_vs_reference_fixture(capi, L, name, mode):
     g = G.load(name)
     ctor = dict(g["meta"]["ctor"])
@@ -194,7 +224,11 @@ def test_module_forward_backward_vs_reference_fixture(capi, L, name, mode):
         assert rel.max().item() <= 1e-5, f"per-frame loss, no-cut: {rel}"
         assert abs(value.item() - g["value"].item()) <= 1e-5 * abs(g["value"].item())
     else:
-        assert abs(value.item() - g["value"].item()) <= 2e-3 * abs(g["value"].item())
+        # cutoff mode: a frame whose target CDF ends within an ulp of 1 keeps or drops its last slots with the
+        # rounding of the CDF (App. B) -- the reference's own fp32 value is that far from its fp64 value
+        v64 = O.sot_loss(g["x"].double(), g["y"].double(), g["pos_x"].double(), g["pos_y"].double(), **kw).item()
+        slack = max(1e-5, 1.5 * abs(g["value"].item() - v64) / abs(v64))
+        assert abs(value.item() - v64) <= slack * abs(v64), (value.item(), g["value"].item(), v64)
 
     # loss and gradients against the fp64 continuation of the KERNEL's CDFs
     xs, ys, pos, perm = _sorted_case(g)
@@ -239,7 +273,12 @@ def test_module_forward_backward_vs_reference_fixture(capi, L, name, mode):
                     np.array_equal(cv[r], g["cv"].reshape(-1, F)[r].numpy()))
             if same:
                 assert abs(rows[r].item() - ref_rows[r].item()) <= 2e-6 * abs(ref_rows[r].item())
-    del ref_gx, ref_gy
+    # (b) the reference's own gradients: CUDA must be as close to the float64 evaluation of the reference's formula
+    # as the reference's float32 autograd (the fixture) is, per fixture
+    t64x, t64y = _ref64_grads(g["x"].reshape(-1, F), g["y"].reshape(-1, F), g["pos_x"], g["pos_y"], kw)
+    t64x, t64y = t64x[:, perm].numpy() * rows.numel(), t64y[:, perm].numpy() * rows.numel()
+    _assert_grad_gate(torch.from_numpy(gx), torch.from_numpy(ref_gx), torch.from_numpy(t64x), f"{name} grad_x")
+    _assert_grad_gate(torch.from_numpy(gy), torch.from_numpy(ref_gy), torch.from_numpy(t64y), f"{name} grad_y")
 
 
 @pytest.mark.parametrize("name", ["sot512_cut", "sot2048_cut", "sot2048_nocut", "sot512_p1_nosquare", "sot512_p3"])
@@ -354,7 +393,7 @@ def test_every_kernel_configuration_gives_the_same_answer(capi, L, tuning):
     g = G.load("sot2048_nocut")
     base = None
     for t in ((0, 0), tuning):
-        capi.set_tuning(*t)
+        _tune(capi, t)
         try:
             mod = L.Wasserstein1D(**g["meta"]["ctor"])
             x = g["x"].to(DEV).requires_grad_(True)
@@ -371,6 +410,44 @@ def test_every_kernel_configuration_gives_the_same_answer(capi, L, tuning):
     assert abs(cur[0] - base[0]) <= 2e-6 * abs(base[0])
     for a, b in ((cur[1], base[1]), (cur[2], base[2])):
         assert (a - b).norm().item() <= 1e-3 * b.norm().item()
+
+
+# ------------------------------------------------------------------------------------------
+# parity at the paper's batch size (1024 frames = 64 signals x 16), all four BASELINE configurations
+# ------------------------------------------------------------------------------------------
+PAPER_CONFIGS = {"SOT-2048": (2048, True, "linear"), "SOT-512": (512, True, "linear"),
+                 "SOT-512-LogF": (512, True, "logf"), "SOT-NoCut": (2048, False, "linear")}
+
+
+@pytest.mark.parametrize("config", sorted(PAPER_CONFIGS))
+@pytest.mark.parametrize("mode", ["onepass", "recompute"])
+def test_parity_at_the_papers_batch_size(L, config, mode):
+    """The module as the trainer calls it (trainer.py:209-221) on 1024 synthetic frames, against the reference's
+    float32 evaluation (the pinned oracle) and its float64 evaluation.  Bounds = the north star's 1e-5 on the batch
+    loss in EVERY mode (measured 1e-7 .. 3.3e-6, profiles/r01j_parity_at_scale.jsonl) and the fp64-relative
+    gradient gate."""
+    from sot_b200 import synthetic as S
+    n_fft, cut, grid = PAPER_CONFIGS[config]
+    x, y = S.sot_batch(64, n_fft, seed=42)
+    pos = S.linear_positions(n_fft) if grid == "linear" else S.logf_positions(n_fft)
+    kw = dict(p=2, square=True, cut_scale=cut, limit=cut)
+    rows32, g32x, g32y = O.sot_loss_and_grads(x, y, pos, pos, stable=True, **kw)
+    rows64, g64x, g64y = O.sot_loss_and_grads(x.double(), y.double(), pos.double(), pos.double(), stable=True, **kw)
+    mod = L.Wasserstein1D(p=2, square_dist=True, dont_normalize=cut, limit_quantile_range=cut, backward_mode=mode)
+    xd, yd = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
+    value = mod(xd, yd, x_pos=pos.to(DEV), y_pos=pos.to(DEV))
+    value.backward()
+    ref_mean = rows32.double().mean().item()
+    assert abs(value.item() - ref_mean) <= 1e-5 * abs(ref_mean), (config, value.item(), ref_mean)
+    with torch.no_grad():
+        rows = mod(x.reshape(-1, 1, x.shape[-1]).to(DEV), y.reshape(-1, 1, y.shape[-1]).to(DEV), x_pos=pos.to(DEV),
+                   y_pos=pos.to(DEV), dims=1).cpu()
+    # per frame: no further from the float64 value than the reference's float32 value is, on average
+    e_mine = (rows.reshape(-1).double() - rows64).abs().mean().item()
+    e_ref = (rows32.double() - rows64).abs().mean().item()
+    assert e_mine <= 1.5 * e_ref + 1e-9, (config, e_mine, e_ref)
+    _assert_grad_gate(xd.grad.cpu().reshape(g64x.shape), g32x, g64x, f"{config} d/dtarget")
+    _assert_grad_gate(yd.grad.cpu().reshape(g64y.shape), g32y, g64y, f"{config} d/dprediction")
 
 
 # ------------------------------------------------------------------------------------------
@@ -399,8 +476,15 @@ def test_hinge_gate_and_threshold(L):
     v = mod(x, y, **g["meta"]["call"])
     v.backward()
     assert torch.allclose(v.cpu(), g["value"], rtol=1e-5, atol=0)
-    for mine, ref in ((x.grad.cpu(), g["grad_x"]), (y.grad.cpu(), g["grad_y"])):
-        assert (mine - ref).norm() <= 2e-3 * ref.norm()
+    ctor, call = g["meta"]["ctor"], g["meta"]["call"]
+    xd = g["x"].double().requires_grad_(True)
+    yd = g["y"].double().requires_grad_(True)
+    grid = torch.linspace(0, 1, ctor["fixed_x"]).double()
+    rows64 = O.sot_per_frame(xd, yd, grid, grid, p=ctor.get("p", 1), square=bool(ctor.get("square_dist", False)),
+                             stable=True)
+    torch.relu(rows64 - call.get("hinge", 0.0)).mean().backward()
+    for mine, ref, t64, nm in ((x.grad.cpu(), g["grad_x"], xd.grad, "x"), (y.grad.cpu(), g["grad_y"], yd.grad, "y")):
+        _assert_grad_gate(mine, ref, t64.reshape(ref.shape), f"hinge grad_{nm}")
         assert torch.equal(mine.reshape(30, -1).abs().sum(1) == 0, ref.reshape(30, -1).abs().sum(1) == 0), "hinge gate"
 
 
