@@ -14,7 +14,7 @@ BENCH="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-ref-cuda"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
     --log-file gpurun_out/launches_r02a.csv $BENCH > gpurun_out/ncu_launch_r02a.log 2>&1
 echo "launch-list exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sot_frame -s 6 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sot_frame -s 3 -c 1 \
     -o gpurun_out/prof_r02a -f $BENCH > gpurun_out/ncu_full_r02a.log 2>&1
 echo "full exit $?"
 ls -la gpurun_out | tail -12
