@@ -16,15 +16,14 @@
 // `sot_set_tuning` are compiled in with -DSOT_TUNING_CONFIGS (`SOT_BUILD_TUNING=1 python -m sot_b200.build`).
 SOT_DECLARE_CONFIG(32, 9, 296, 1)
 SOT_DECLARE_CONFIG(64, 9, 584, 2)
-SOT_DECLARE_CONFIG(64, 17, 1032, 1)
+SOT_DECLARE_CONFIG(64, 17, 1096, 1)
 SOT_DECLARE_CONFIG(128, 9, 1160, 1)
 SOT_DECLARE_CONFIG(128, 17, 2184, 2)
 SOT_DECLARE_CONFIG(256, 17, 4360, 2)
 SOT_DECLARE_CONFIG(256, 33, 8456, 1)
 #ifdef SOT_TUNING_CONFIGS
 SOT_DECLARE_CONFIG(32, 9, 296, 2)
-SOT_DECLARE_CONFIG(64, 17, 1032, 2)
-SOT_DECLARE_CONFIG(128, 9, 1032, 1)
+SOT_DECLARE_CONFIG(64, 17, 1096, 2)
 SOT_DECLARE_CONFIG(32, 33, 1064, 2)
 SOT_DECLARE_CONFIG(32, 33, 1064, 1)
 #endif
@@ -121,11 +120,10 @@ struct Config {
 const Config kConfigs[] = {
     {32, 9, 296, 1, sot_launch_32_9_296_1},      // <= 288 bins   (n_fft 512: 257)
     {64, 9, 584, 2, sot_launch_64_9_584_2},      // <= 576 bins   (n_fft 1024: 513)
-    {64, 17, 1032, 1, sot_launch_64_17_1032_1},  // <= 1025 bins  (n_fft 2048: 1025) -- measured best of the five
+    {64, 17, 1096, 1, sot_launch_64_17_1096_1},  // <= 1088 bins  (n_fft 2048: 1025) -- measured best of the five
 #ifdef SOT_TUNING_CONFIGS
     {32, 9, 296, 2, sot_launch_32_9_296_2},      // two-chain variant: measured slower
-    {64, 17, 1032, 2, sot_launch_64_17_1032_2},  // alternatives for 1025 bins (profiles/r01j_tuning_experiments.txt)
-    {128, 9, 1032, 1, sot_launch_128_9_1032_1},
+    {64, 17, 1096, 2, sot_launch_64_17_1096_2},  // alternatives for 1025 bins (profiles/r01j_tuning_experiments.txt)
     {32, 33, 1064, 2, sot_launch_32_33_1064_2},
     {32, 33, 1064, 1, sot_launch_32_33_1064_1},  // one warp per frame, one chain: the loss-only kernel is 8 % faster
                                                  // than 64 x 17, the gradient kernel 20 % slower -- 168 registers

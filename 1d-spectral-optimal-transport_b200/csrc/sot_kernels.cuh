@@ -136,8 +136,7 @@ struct Layout {
     // small per-CTA structures first, the rows after them: a thread whose bins lie past the end of a row reads
     // (and masks) whatever follows -- after the last row that is the PAD below, never live scratch data
     static constexpr uint32_t SCRATCH = 0;                        // 8 doubles per warp
-    static constexpr uint32_t MBOX = SCRATCH + 64u * (TPF / 32);  // (first q, first m*d) per chunk + end marker
-    static constexpr uint32_t CARRY = MBOX + 8u * (NCH * TPF + 1);
+    static constexpr uint32_t CARRY = SCRATCH + 64u * (TPF / 32);  // m*d of the group open at the end of each chunk
     static constexpr uint32_t MBAR = (CARRY + 4u * NCH * TPF + 15u) & ~15u;
     static constexpr uint32_t HEAD = (MBAR + 16u + 127u) & ~127u;
     static constexpr uint32_t A = HEAD, B = HEAD + ROW;  // CDF rows (also the landing zone of the raw rows)
@@ -154,7 +153,7 @@ struct Layout {
     static constexpr uint32_t LAND = CPLX ? HEAD + REAL_ROWS * ROW : A;
     static constexpr uint32_t LAND_ROW = CPLX ? 2 * ROW : ROW;  // bytes between the u and the v landing row
     static constexpr uint32_t ROWS = REAL_ROWS + (CPLX ? 4 : 0);
-    static constexpr uint32_t PAD = ROW / 4 + 64u;  // over-read room after the last row (TPF * E bins >= a row)
+    static constexpr uint32_t PAD = 64u;  // (rows hold TPF * E entries and the lead: nothing is read past the last row)
     static constexpr uint32_t TOTAL = HEAD + ROWS * ROW + PAD;
     static constexpr int MAX_BINS = RS - 7;  // sentinel + up to 3 floats of lead + rounding of the bulk window
 };
@@ -281,6 +280,26 @@ SOT_DEVINL void advance_uni(float& a, float& d, float& b, uint32_t& adrA, uint32
         : "f"(h), "f"(neg_h), "f"(k.one), "f"(k.nz), "f"(k.one_b), "f"(k.nz_b));
 }
 
+// One step of the merge-path bit descent, branch free: probe co-rank min(cur + STEP, hi) -- clamping instead of
+// skipping keeps the descent correct (the predicate "A[i-1] <= B[k0-i]" is monotone in i: once hi itself passes,
+// every later probe is hi again) and every probe address valid, so the two loads need no guard (a guarded pair
+// costs BSSY / BSYNC / BRA per step and branch-resolving stalls over 11 dependent rounds).
+// sum = addr(A[i]) + addr(B[k0-i]), constant along a diagonal.
+template <int STEP>
+SOT_DEVINL void search_step(uint32_t& cur, uint32_t hi, uint32_t sum) {
+    const uint32_t cand = min(cur + 4u * STEP, hi);
+    const float av = lds32(cand - 4);    // A[i-1] for the candidate i (i = lo = 0 is never probed: cand > cur >= A0
+    const float bv = lds32(sum - cand);  //  unless hi == cur, and then the row's left neighbour in shared memory is read
+    cur = (av <= bv) ? cand : cur;       //  and the outcome is the same position)
+}
+// the whole descent for NCH interleaved searches: steps TOP, TOP/2, ..., 1 (elements)
+template <int STEP, int NCH>
+SOT_DEVINL void search_descent(uint32_t (&cur)[NCH], const uint32_t (&hi)[NCH], const uint32_t (&sum)[NCH]) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) search_step<STEP>(cur[ch], hi[ch], sum[ch]);
+    if constexpr (STEP > 1) search_descent<STEP / 2, NCH>(cur, hi, sum);
+}
+
 // fp64 reciprocal of a positive float >= 1e-7: hardware approximation + two Newton steps
 SOT_DEVINL double recip_f64(float x) {
     const double xd = static_cast<double>(x);
@@ -299,31 +318,20 @@ SOT_DEVINL void cta_sync() {
     }
 }
 
-// One Hillis-Steele step of a warp scan of an fp64 value: two 32-bit shuffles whose "source lane in range"
-// predicate guards the add (what the compiler makes of __shfl_up_sync(double) costs three times as much).
-template <bool REVERSE, int OFF>
-SOT_DEVINL void scan_step(double& v) {
-    if constexpr (REVERSE) {
-        asm volatile(
-            "{\n .reg .b32 lo, hi, ylo, yhi;\n .reg .f64 y;\n .reg .pred p;\n"
-            " mov.b64 {lo, hi}, %0;\n"
-            " shfl.sync.down.b32 ylo|p, lo, %1, 0x1f, 0xffffffff;\n"
-            " shfl.sync.down.b32 yhi, hi, %1, 0x1f, 0xffffffff;\n"
-            " mov.b64 y, {ylo, yhi};\n"
-            " @p add.f64 %0, %0, y;\n}"
-            : "+d"(v)
-            : "n"(OFF));
-    } else {
-        asm volatile(
-            "{\n .reg .b32 lo, hi, ylo, yhi;\n .reg .f64 y;\n .reg .pred p;\n"
-            " mov.b64 {lo, hi}, %0;\n"
-            " shfl.sync.up.b32 ylo|p, lo, %1, 0x0, 0xffffffff;\n"
-            " shfl.sync.up.b32 yhi, hi, %1, 0x0, 0xffffffff;\n"
-            " mov.b64 y, {ylo, yhi};\n"
-            " @p add.f64 %0, %0, y;\n}"
-            : "+d"(v)
-            : "n"(OFF));
-    }
+// One Hillis-Steele step of a warp scan of an fp64 value that is carried as an EXCLUSIVE scan: the lane at the
+// edge (lane 0; lane 31 when REVERSE) holds 0.0 from start to end, so a lane whose partner would lie outside the
+// warp reads that lane instead (`src` = clamped partner lane) and adds 0.0 -- an unconditional add.  (A predicated
+// fp64 add costs DADD + 2 FSEL + moves after ptxas; `__shfl_up_sync(double)` three times as much.)
+SOT_DEVINL void scan_step(double& v, int src) {
+    asm volatile(
+        "{\n .reg .b32 lo, hi, ylo, yhi;\n .reg .f64 y;\n"
+        " mov.b64 {lo, hi}, %0;\n"
+        " shfl.sync.idx.b32 ylo, lo, %1, 0x1f, 0xffffffff;\n"
+        " shfl.sync.idx.b32 yhi, hi, %1, 0x1f, 0xffffffff;\n"
+        " mov.b64 y, {ylo, yhi};\n"
+        " add.f64 %0, %0, y;\n}"
+        : "+d"(v)
+        : "r"(src));
 }
 // Exclusive scans (prefix; suffix when REVERSE) over the TPF threads of the CTA of two fp32 values, carried
 // in fp64.  ta, tb: my values; returns my exclusive offsets and the CTA totals.  One CTA barrier when the
@@ -341,16 +349,12 @@ SOT_DEVINL void cta_scan2(float ta, float tb, double& off_a, double& off_b, doub
     float sb = REVERSE ? __shfl_down_sync(FULL_MASK, tb, 1) : __shfl_up_sync(FULL_MASK, tb, 1);
     double ea = lane == edge ? 0.0 : static_cast<double>(sa);
     double eb = lane == edge ? 0.0 : static_cast<double>(sb);
-    scan_step<REVERSE, 1>(ea);
-    scan_step<REVERSE, 1>(eb);
-    scan_step<REVERSE, 2>(ea);
-    scan_step<REVERSE, 2>(eb);
-    scan_step<REVERSE, 4>(ea);
-    scan_step<REVERSE, 4>(eb);
-    scan_step<REVERSE, 8>(ea);
-    scan_step<REVERSE, 8>(eb);
-    scan_step<REVERSE, 16>(ea);
-    scan_step<REVERSE, 16>(eb);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int src = REVERSE ? min(lane + off, 31) : max(lane - off, 0);
+        scan_step(ea, src);
+        scan_step(eb, src);
+    }
     // warp totals, formed on the last lane of the scan direction
     const double wa_mine = ea + static_cast<double>(ta), wb_mine = eb + static_cast<double>(tb);
     if constexpr (NW == 1) {
@@ -452,7 +456,7 @@ SOT_DEVINL void cta_scan2d(double& a, double& b, double& total_a, double& total_
 constexpr int min_ctas(int tpf, int e, int smem_bytes, int out) {
     const int by_smem = (227 * 1024) / (smem_bytes + 1024);
 #ifndef SOT_REGS_GRAD_E17  // (tuning experiments: -DSOT_REGS_GRAD_E17=.. -DSOT_REGS_LOSS_E17=..)
-#define SOT_REGS_GRAD_E17 96
+#define SOT_REGS_GRAD_E17 128
 #endif
 #ifndef SOT_REGS_LOSS_E17
 #define SOT_REGS_LOSS_E17 64
@@ -530,6 +534,7 @@ template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int O
 __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH, UNI, CPLX>::TOTAL, OUT))
     sot_frame_kernel(const FrameArgs args) {
     static_assert(NCH == 1 || NCH == 2, "one or two merge chains per thread");
+    static_assert(RS >= TPF * E + 8, "rows hold every thread's E entries (stored without guards) plus the lead / sentinel");
     static_assert(!(UNI && OUT == OUT_PLAN), "the plan emitter always reads positions");
     static_assert(!CPLX || (MODE == MODE_SPECTRA && OUT != OUT_PLAN), "complex input: loss / gradient from spectra only");
     constexpr bool FROM_BINS = (MODE != MODE_CDF);  // spectra or raw weights: the kernel builds the CDFs
@@ -564,7 +569,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     float* const fsm = reinterpret_cast<float*>(smem);
     double* const scratch = reinterpret_cast<double*>(smem + LY::SCRATCH);
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem + LY::MBAR);
-    const uint32_t mbox = sb + LY::MBOX, carry = sb + LY::CARRY;
+    const uint32_t carry = sb + LY::CARRY;
     const bool in_u = e0 + E <= n, in_v = e0 + E <= m;  // all of my E bins exist (no guards needed)
 
     // The K merged slots are cut into NCH * TPF chunks of L consecutive slots; thread t walks chunks
@@ -584,7 +589,6 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     if (tid == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
-        sts64(mbox + 8u * NCHUNK, f_inf(), 0.0f);  // virtual slot K: a new group with m*d = 0
     }
     float pu0 = 0.0f, pv0 = 0.0f, hstep = 0.0f;  // (UNI) pos_u[i] = pu0 + i*hstep, pos_v[j] = pv0 + j*hstep
     if constexpr (UNI) {
@@ -659,6 +663,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         float acc[NCH] = {};  // my part of the frame's loss
         bool finite = true;  // masses (and the scaled totals) are finite numbers
         double inv_u = 1.0, inv_v = 1.0;
+        double base_mass_u = 0.0, base_mass_v = 0.0;  // sum of the (unnormalised) weights of the threads before me
         bool u_live = false, v_live = false;  // mass above the safe_divide floor -> carries gradient
         f32x2 x2[E];  // my (u, v) bin pairs (the gradient kernel needs them again at the end)
         int saved_corank[NCH];                // (loaded early: the global-memory latency hides behind stage 2)
@@ -666,6 +671,8 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         for (int ch = 0; ch < NCH; ++ch)
             saved_corank[ch] = args.coranks_in != nullptr ? min(static_cast<int>(args.coranks_in[frame * NCHUNK + NCH * tid + ch]), n) : 0;
         (void)inv_v;
+        (void)base_mass_u;
+        (void)base_mass_v;
         (void)u_live;
         (void)v_live;
 
@@ -724,6 +731,8 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 // (the barrier inside also orders the raw reads before the CDF writes)
                 cta_scan2<TPF, false, true>(Tu, Tv, off_u, off_v, nxt_u, nxt_v, tot_u, tot_v, scratch, tid);
             }
+            base_mass_u = off_u;
+            base_mass_v = off_v;
             const float mass_u = static_cast<float>(tot_u), mass_v = static_cast<float>(tot_v);
             u_live = mass_u > SAFE_EPS;  // utils.py:137: den <= eps -> eps
             v_live = mass_v > SAFE_EPS;
@@ -759,24 +768,22 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 const float cap_u = static_cast<float>(nxt_u * inv_u), cap_v = static_cast<float>(nxt_v * inv_v);
                 const f32x2 bh2 = pack2(bh_u, bh_v), bl2 = pack2(bl_u, bl_v);
                 const f32x2 inv2 = pack2(static_cast<float>(inv_u), static_cast<float>(inv_v));
-                auto emit = [&](auto SQ, auto INSIDE) {
+                // Every thread stores all E entries (rows hold TPF * E floats and more): no per-element guards, one
+                // code path -- the few threads whose bins straddle or lie past the end of a row used to drag
+                // their whole warp through a second, guarded copy of this loop.  What they wrote past the row is
+                // overwritten below (sentinels).
+                auto emit = [&](auto SQ) {
                     f32x2 p2 = 0;
 #pragma unroll
                     for (int c = 0; c < E; ++c) {
                         p2 = decltype(SQ)::value ? fma2(x2[c], x2[c], p2) : add2(p2, x2[c]);
                         float ca, cb;
                         unpack2(add2(fma2(p2, inv2, bl2), bh2), ca, cb);
-                        if (decltype(INSIDE)::value || e0 + c < n) sts32(A0 + 4 * (e0 + c), fminf(ca, cap_u));
-                        if (decltype(INSIDE)::value || e0 + c < m) sts32(B0 + 4 * (e0 + c), fminf(cb, cap_v));
+                        sts32(A0 + 4 * (e0 + c), fminf(ca, cap_u));
+                        sts32(B0 + 4 * (e0 + c), fminf(cb, cap_v));
                     }
                 };
-                using T_ = std::true_type;
-                using F_ = std::false_type;
-                if (sq) {  // (uniform branches)
-                    if (inside) emit(T_{}, T_{}); else emit(T_{}, F_{});
-                } else {
-                    if (inside) emit(F_{}, T_{}); else emit(F_{}, F_{});
-                }
+                if (sq) emit(std::true_type{}); else emit(std::false_type{});  // (uniform branch)
             }
             // NaN / inf anywhere (or an overflowing cut-mode scale) poisons the frame: the walk is skipped
             // (its +inf sentinels must stay unique) and NaN is written instead
@@ -797,11 +804,25 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 if (e0 + c < m) sts32(B0 + 4 * (e0 + c), fminf(xv[c], FLT_BIG));
             }
         }
-        if (tid == 0) {
-            sts32(A0 + 4 * n, f_inf());
-            sts32(B0 + 4 * m, f_inf());
+        // +inf sentinels at [n] / [m]: written by the thread whose bins hold that index, AFTER its own stores
+        // (program order), or by thread 0 when no thread's bins reach that far
+        if ((e0 <= n && n < e0 + E) || (tid == 0 && n >= TPF * E)) sts32(A0 + 4 * n, f_inf());
+        if ((e0 <= m && m < e0 + E) || (tid == 0 && m >= TPF * E)) sts32(B0 + 4 * m, f_inf());
+        if constexpr (WITH_GRAD) {
+            // the previous frame's output store must have finished READING its staging rows (the dL/dCDF rows)
+            // before anybody writes them again (below, in the walk, or in stage 4 of a poisoned frame): thread 0
+            // waits for that before it arrives at the barrier.  The store has had two stages to drain.
+            if (tid == 0) bulk_wait_read_all();
         }
         cta_sync<TPF>();
+        if constexpr (WITH_GRAD && FROM_BINS) {
+            // the gradient stage sums dL/dCDF over all E entries of every thread without guards: zero what lies
+            // past the end of the rows (the walk only writes real entries)
+            if (!in_u)
+                for (int idx = max(n, e0); idx < e0 + E; ++idx) sts32o<LY::G_OFF>(A0 + 4 * idx, 0.0f);
+            if (!in_v)
+                for (int idx = max(m, e0); idx < e0 + E; ++idx) sts32o<LY::G_OFF>(B0 + 4 * idx, 0.0f);
+        }
 
         uint32_t adrA[NCH], adrB[NCH];
         float a[NCH], pa[NCH], b[NCH], pb[NCH], qprev[NCH];
@@ -828,18 +849,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 hiA[ch] = A0 + 4u * min(k0[ch], n);
                 sumAB[ch] = A0 + B0 + 4u * k0[ch];  // addr(A[i]) + addr(B[k0-i]) is constant
             }
-#pragma unroll
-            for (int step = SEARCH_TOP; step >= 1; step >>= 1) {
-#pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    const uint32_t cand = cur[ch] + 4u * step;
-                    if (cand <= hiA[ch]) {
-                        const float av = lds32(cand - 4);          // A[i-1] for the candidate i
-                        const float bv = lds32(sumAB[ch] - cand);  // B[k0-i]
-                        if (av <= bv) cur[ch] = cand;
-                    }
-                }
-            }
+            search_descent<SEARCH_TOP, NCH>(cur, hiA, sumAB);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) i0[ch] = static_cast<int>((cur[ch] - A0) >> 2);
         }
@@ -907,11 +917,6 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             // slot: G = (m*d)_group - (m*d)_next group.  It is stored one step later,
             // when the next slot is known.  (It cannot overwrite the consumed CDF entry or its position:
             // a slower thread may still load that entry as the head that ends its own range.)
-            // the previous frame's output store must have finished READING its staging rows (the dL/dCDF
-            // rows) before they are written again (walk, or stage 4 of a poisoned frame); every such write
-            // is behind a barrier that thread 0 reaches after this wait.  By now the store has had two
-            // stages to drain.
-            if (tid == 0) bulk_wait_read_all();
             if (finite) {
                 float md_prev[NCH];
                 bool inherited[NCH];  // the open group started before my chunk: its m*d is not known yet
@@ -921,9 +926,6 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     const float q = fminf(a[ch], b[ch]);
                     const float D = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
                     const float fm = (q > thr) ? 0.0f : D;
-                    // what the chunk on my left needs to close ITS last slot: my first value and the m*d my
-                    // first slot has if it opens a group (empty chunk: the end marker)
-                    sts64(mbox + 8u * (NCH * tid + ch), cnt[ch] > 0 ? q : f_inf(), cnt[ch] > 0 ? fm : 0.0f);
                     inherited[ch] = (k0[ch] > 0) && (q == qprev[ch]);
                     md_prev[ch] = inherited[ch] ? 0.0f : fm;
                     float dq = q - qprev[ch];
@@ -935,7 +937,6 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     consumed[ch] = 0;
                     fix[ch] = NO_FIX;
                 }
-                cta_sync<TPF>();  // mailbox complete (and thread 0 has seen the previous output store drain)
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch)
                     if (cnt[ch] > 0) {
@@ -978,9 +979,13 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 for (int ch = 0; ch < NCH; ++ch) {
                     float carry_out = -1.0f;  // -1 = "my whole chunk continues a group opened before it"
                     if (cnt[ch] > 0) {
-                        // the slot after my chunk: first slot of the next chunk, or the end marker
-                        float qn, mdn;
-                        lds64(mbox + 8u * (NCH * tid + ch + 1), qn, mdn);
+                        // The slot after my chunk = the first slot of the next chunk (or the virtual slot K: both
+                        // heads are the +inf sentinels, a new group with m*d = 0): my heads after the last advance
+                        // ARE that slot -- the same shared-memory entries and the same position difference the
+                        // next chunk starts from, so no mailbox between the chunks (and no barrier for it).
+                        const float qn = fminf(a[ch], b[ch]);
+                        const float Dn = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
+                        const float mdn = (qn > thr) ? 0.0f : Dn;
                         const bool same = (qn == qprev[ch]);
                         const float md = same ? md_prev[ch] : mdn;
                         sts32o<LY::G_OFF>(consumed[ch], md_prev[ch] - md);
@@ -1072,10 +1077,24 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         }
 
         // ---- loss of the frame: fp32 partials, summed in fp64 ---------------------------------------
-        {
-            double part = static_cast<double>(NCH == 2 ? acc[0] + acc[NCH - 1] : acc[0]);
+        // (gradient kernel from spectra: the cross-warp half of this reduction shares ONE barrier with the suffix
+        // scan and the mass-term sums of stage 4, see below)
+        constexpr bool MERGED = WITH_GRAD && FROM_BINS;
+        double part = 0.0;
+        auto reduce_loss_in_warp = [&]() {
+            part = static_cast<double>(NCH == 2 ? acc[0] + acc[NCH - 1] : acc[0]);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULL_MASK, part, off);
+        };
+        auto write_loss = [&]() {
+            if (tid == 0) {
+                const float frame_loss = finite ? static_cast<float>(part) : f_nan();
+                if (args.loss != nullptr) args.loss[frame] = frame_loss;
+                cta_loss += static_cast<double>(frame_loss);
+            }
+        };
+        if constexpr (!MERGED) {
+            reduce_loss_in_warp();
             if constexpr (NW > 1) {
                 if ((tid & 31) == 0) scratch[2 * NW + (tid >> 5)] = part;
                 __syncthreads();  // (forward / plan: also "every thread is done with the CDF rows")
@@ -1085,11 +1104,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             } else {
                 __syncwarp();
             }
-            if (tid == 0) {
-                const float frame_loss = finite ? static_cast<float>(part) : f_nan();
-                if (args.loss != nullptr) args.loss[frame] = frame_loss;
-                cta_loss += static_cast<double>(frame_loss);
-            }
+            write_loss();
         }
 
         if constexpr (!WITH_GRAD) {
@@ -1107,39 +1122,37 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             constexpr uint32_t STAGE_U = CPLX ? LY::LAND : LY::A + LY::G_OFF;
             constexpr uint32_t STAGE_V = CPLX ? LY::LAND + LY::LAND_ROW : LY::B + LY::G_OFF;
             if constexpr (FROM_BINS) {
-                // cumsum transpose (suffix sums of dL/dCDF) and the normalisation chain rule.
-                // sum_i gw_i w_i = sum_i (dL/dc_i) c_i (Abel summation), so the mass term needs only the
-                // CDF values and dL/dCDF that are already in shared memory.
+                // cumsum transpose: gw_i = sum_{l >= i} dL/dc_l = (sum of the threads after me) + local suffix sum
+                // ls_i, and the normalisation chain rule, whose mass term is  sum_i gw_i w_i  -- the sum the
+                // reference's autograd forms (w = x^2 / M, losses.py:176-184).  Per thread
+                //     sum_i gw_i w_i = off * (T / M) + sum_i ls_i w_i,
+                // and over the CTA  sum_t off_t T_t = sum_t S_t P_t  (S_t = my sum of dL/dc, P_t = the sum of the
+                // T before me = the base of my CDF entries, kept from stage 2): every term is thread local, so ONE
+                // barrier carries the suffix scan, these sums and the loss.  Nothing is read back from the CDF rows
+                // (their past-the-end entries are +inf) and their shared-memory traffic is gone.
                 // (packed fp32 on (u, v) pairs, like the CDF stage)
                 f32x2 ls2[E];
                 f32x2 s2 = 0, d2 = 0;
-                const bool inside = in_u && in_v;
-                if (inside) {
+                const bool sqw = square && !CPLX;  // x2 holds magnitudes: w ~ x^2; else x2 is what was accumulated
 #pragma unroll
-                    for (int c = E - 1; c >= 0; --c) {
-                        const f32x2 g2 = lds32x2(GA0 + 4 * (e0 + c), GB0 + 4 * (e0 + c));
-                        s2 = add2(s2, g2);
-                        d2 = fma2(g2, lds32x2(A0 + 4 * (e0 + c), B0 + 4 * (e0 + c)), d2);
-                        ls2[c] = s2;
-                    }
-                } else {  // (reads past a row stay inside shared memory; the garbage is masked)
+                for (int c = E - 1; c >= 0; --c) {
+                    s2 = add2(s2, lds32x2(GA0 + 4 * (e0 + c), GB0 + 4 * (e0 + c)));
+                    ls2[c] = s2;
+                }
+                if (sqw) {
 #pragma unroll
-                    for (int c = E - 1; c >= 0; --c) {
-                        const f32x2 g2 = mask2(lds32x2(GA0 + 4 * (e0 + c), GB0 + 4 * (e0 + c)), e0 + c < n, e0 + c < m);
-                        const f32x2 c2 = mask2(lds32x2(A0 + 4 * (e0 + c), B0 + 4 * (e0 + c)), e0 + c < n, e0 + c < m);
-                        s2 = add2(s2, g2);
-                        d2 = fma2(g2, c2, d2);
-                        ls2[c] = s2;
-                    }
+                    for (int c = 0; c < E; ++c) d2 = fma2(mul2(x2[c], x2[c]), ls2[c], d2);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < E; ++c) d2 = fma2(x2[c], ls2[c], d2);
                 }
                 float su, sv, du, dv;
                 unpack2(s2, su, sv);
                 unpack2(d2, du, dv);
-                double off_u, off_v, nu_ = 0.0, nv_ = 0.0, tu, tv;
-                cta_scan2<TPF, true, false>(su, sv, off_u, off_v, nu_, nv_, tu, tv, scratch + 4 * NW, tid);
-                (void)nu_;
-                (void)nv_;
-                double dot_u = static_cast<double>(du), dot_v = static_cast<double>(dv);
+                // my share of sum_i gw_i w_i (the factor 1/M is applied once, below: inv_u / inv_v)
+                reduce_loss_in_warp();
+                double dot_u = static_cast<double>(su) * base_mass_u + static_cast<double>(du);
+                double dot_v = static_cast<double>(sv) * base_mass_v + static_cast<double>(dv);
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
                     dot_u += __shfl_xor_sync(FULL_MASK, dot_u, off);
@@ -1147,22 +1160,33 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 }
                 if constexpr (NW > 1) {
                     if ((tid & 31) == 0) {
+                        scratch[2 * NW + (tid >> 5)] = part;
                         scratch[6 * NW + (tid >> 5)] = dot_u;
                         scratch[7 * NW + (tid >> 5)] = dot_v;
                     }
-                    __syncthreads();
+                }
+                double off_u, off_v, nu_ = 0.0, nv_ = 0.0, tu, tv;
+                cta_scan2<TPF, true, false>(su, sv, off_u, off_v, nu_, nv_, tu, tv, scratch + 4 * NW, tid);  // (barrier)
+                (void)nu_;
+                (void)nv_;
+                if constexpr (NW > 1) {
+                    part = 0.0;
                     dot_u = 0.0;
                     dot_v = 0.0;
 #pragma unroll
                     for (int k = 0; k < NW; ++k) {
+                        part += scratch[2 * NW + k];
                         dot_u += scratch[6 * NW + k];
                         dot_v += scratch[7 * NW + k];
                     }
                 } else {
                     __syncwarp();
                 }
-                // every thread has read its CDF and dL/dCDF entries (barriers above): the CDF rows can take
-                // the next frame, the dL/dCDF rows the finished gradients
+                write_loss();
+                dot_u *= inv_u;
+                dot_v *= inv_v;
+                // every thread has read its dL/dCDF entries and is done with the CDF rows (barrier above): the CDF
+                // rows can take the next frame, the dL/dCDF rows the finished gradients
                 if constexpr (!CPLX) {  // (complex: the landing rows are the output staging, see below)
                     if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
                 }
@@ -1178,24 +1202,20 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 if constexpr (!CPLX) {
                     const f32x2 b2 = pack2(bu, bv), k2 = pack2(ku, kv);
                     const uint32_t out_u = GA0 + lead_u + 4 * e0, out_v = GB0 + lead_v + 4 * e0;
-                    auto emit = [&](auto SQ, auto INSIDE) {  // (uniform choices hoisted out of the element loop)
+                    // (uniform choice hoisted out of the element loop; all E entries are stored: what lies past the
+                    // row stays in the staging row)
+                    auto emit = [&](auto SQ) {
 #pragma unroll
                         for (int c = 0; c < E; ++c) {
                             f32x2 g2 = mul2(add2(b2, ls2[c]), k2);
                             if constexpr (decltype(SQ)::value) g2 = mul2(g2, x2[c]);
                             float ga, gb;
                             unpack2(g2, ga, gb);
-                            if (decltype(INSIDE)::value || e0 + c < n) sts32(out_u + 4 * c, ga);
-                            if (decltype(INSIDE)::value || e0 + c < m) sts32(out_v + 4 * c, gb);
+                            sts32(out_u + 4 * c, ga);
+                            sts32(out_v + 4 * c, gb);
                         }
                     };
-                    using T_ = std::true_type;
-                    using F_ = std::false_type;
-                    if (square) {
-                        if (inside) emit(T_{}, T_{}); else emit(T_{}, F_{});
-                    } else {
-                        if (inside) emit(F_{}, T_{}); else emit(F_{}, F_{});
-                    }
+                    if (square) emit(std::true_type{}); else emit(std::false_type{});
                 } else {
                     // d|z|^2/dz = 2z, d|z|/dz = z/|z| (0 at 0, like torch.abs): dL/dz = f * z, written over z.
                     // One row at a time; if the destination's phase differs from the source's the row moves

@@ -6,5 +6,5 @@ for lib in default $PKG/_lib/variants/*.so; do
   python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu "$@" 2>/dev/null | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); r = d['roofline']
-print('$lib', round(d['value']/1e6, 2), 'Mframes/s step', round(d['ms_per_step'], 4), 'bwd', round(r['kernel_ms'], 4), 'fwd', round(r['forward_kernel']['ms'], 4))"
+print('$lib', round(d['value']/1e6, 2), 'Mframes/s step', round(d['ms_per_step'], 4), 'bwd', round(r['kernel_ms'], 4), 'fwd', round(r['forward_only_kernel']['ms'], 4))"
 done

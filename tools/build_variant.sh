@@ -5,9 +5,9 @@
 set -e
 TAG=$1; shift
 PKG=/root/repo/1d-spectral-optimal-transport_b200
-mkdir -p $PKG/_lib/variants /tmp/sot_variant_$TAG
+mkdir -p $PKG/_lib/variants /root/repo/gpurun_out/scratch/sot_variant_$TAG
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v "$@" \
-    -c $PKG/csrc/sot_cfg_64_17_1032_1.cu -o /tmp/sot_variant_$TAG/cfg.o 2> /tmp/sot_variant_$TAG/ptxas.log
-OBJS=$(ls $PKG/build/*.o | grep -v sot_cfg_64_17_1032_1.o)
-nvcc -shared -o $PKG/_lib/variants/libsot_$TAG.so /tmp/sot_variant_$TAG/cfg.o $OBJS -gencode arch=compute_100a,code=sm_100a
-grep -A1 "ILi64ELi17ELi1032ELi1ELb1ELb0ELi2ELi[01]ELi0" /tmp/sot_variant_$TAG/ptxas.log | grep -E "Used|spill" | head -4
+    -c $PKG/csrc/sot_cfg_64_17_1096_1.cu -o /root/repo/gpurun_out/scratch/sot_variant_$TAG/cfg.o 2> /root/repo/gpurun_out/scratch/sot_variant_$TAG/ptxas.log
+OBJS=$(ls $PKG/build/*.o | grep -v sot_cfg_64_17_1096_1.o)
+nvcc -shared -o $PKG/_lib/variants/libsot_$TAG.so /root/repo/gpurun_out/scratch/sot_variant_$TAG/cfg.o $OBJS -gencode arch=compute_100a,code=sm_100a
+grep -A1 "ILi64ELi17ELi1096ELi1ELb1ELb0ELi2ELi[01]ELi0" /root/repo/gpurun_out/scratch/sot_variant_$TAG/ptxas.log | grep -E "Used|spill" | head -4
