@@ -156,6 +156,24 @@ def _stream(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _on_device:
+    """`torch.cuda.device(dev)` only when `dev` is not the current device already (the guard costs ~10 us of host
+    time per call, which matters for launch-bound shards)."""
+
+    def __init__(self, device):
+        self.guard = None if device.index is None or device.index == torch.cuda.current_device() else \
+            torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            return self.guard.__exit__(*exc)
+        return False
+
+
 def make_problem(u, v, pos_u, pos_v, p: float, flags: int) -> SotProblem:
     """u: (N, n), v: (N, m) contiguous CUDA float32; pos_*: (n,) shared or (N, n) per frame.
 
@@ -290,16 +308,21 @@ def mean_step(u, v, pos_u, pos_v, p, flags, grad_scale: float, mean_scale: float
     keep = None
     if post is not None:
         ptrs, rank, seq = post
-        keep = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(q)) for q in ptrs])
-        plan.post_mailboxes, plan.post_world, plan.post_rank = keep, len(ptrs), int(rank)
+        keep = ptrs if isinstance(ptrs, ctypes.Array) else mailbox_array(ptrs)
+        plan.post_mailboxes, plan.post_world, plan.post_rank = keep, len(keep), int(rank)
         if isinstance(seq, torch.Tensor):
             plan.post_seq, plan.post_seq_device = 0, seq.data_ptr()
         else:
             plan.post_seq = int(seq)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.sot_mean_step_device(ctypes.byref(prob), ctypes.byref(plan), _ptr(rows), _ptr(gu), _ptr(gv),
                                         _stream(dev)))
     return mean, rows, gu, gv
+
+
+def mailbox_array(ptrs):
+    """ctypes array of the peers' mailbox pointers (build it once, pass it to every call)."""
+    return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(q)) for q in ptrs])
 
 
 def scale_inplace(a, b, scale) -> None:
@@ -319,7 +342,7 @@ def scale_inplace(a, b, scale) -> None:
             raise ValueError("sot_b200: rows to scale must be contiguous and on the scale's device")
         views.append(torch.view_as_real(t) if t.is_complex() else t)
     va, vb = views
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.sot_scale_inplace_device(_ptr(va), 0 if va is None else va.numel(), _ptr(vb),
                                             0 if vb is None else vb.numel(), _ptr(scale), _stream(dev)))
 
@@ -474,20 +497,22 @@ def p2p_allreduce(values, out, mailbox_ptrs, rank: int, seq: int):
 
 
 def p2p_wait_mean(mailbox_ptrs, rank: int, seq, expected_count: float = 0.0, status_ptr: int = 0,
-                  timeout_ms: int = 0, device=None) -> torch.Tensor:
+                  timeout_ms: int = 0, device=None, stream=None, out=None) -> torch.Tensor:
     """Collects call `seq` of every rank from this rank's mailbox (the stores were made by the last CTA of
-    `mean_step(..., post=...)` on every rank) and returns the global mean, a 0-dim float32 tensor."""
+    `mean_step(..., post=...)` on every rank) and returns the global mean, a 0-dim float32 tensor.  `stream`: a
+    `torch.cuda.Stream` to launch on (default: the current one); `out`: where to write (default: a new tensor)."""
     lib = load()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    out = torch.empty((), dtype=torch.float32, device=dev)
-    world = len(mailbox_ptrs)
-    arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(q)) for q in mailbox_ptrs])
-    with torch.cuda.device(dev):
-        on_device = isinstance(seq, torch.Tensor)  # one-element int64 device tensor: the previous call number
+    if out is None:
+        out = torch.empty((), dtype=torch.float32, device=dev)
+    arr = mailbox_ptrs if isinstance(mailbox_ptrs, ctypes.Array) else mailbox_array(mailbox_ptrs)
+    handle = _stream(dev) if stream is None else ctypes.c_void_p(stream.cuda_stream)
+    on_device = isinstance(seq, torch.Tensor)  # one-element int64 device tensor: the previous call number
+    with _on_device(dev):
         _check(lib.sot_p2p_wait_mean_device(_ptr(out), float(expected_count),
-                                            ctypes.c_void_p(status_ptr) if status_ptr else None, arr, world,
+                                            ctypes.c_void_p(status_ptr) if status_ptr else None, arr, len(arr),
                                             int(rank), 0 if on_device else int(seq), _ptr(seq) if on_device else None,
-                                            int(timeout_ms), _stream(dev)))
+                                            int(timeout_ms), handle))
     return out
 
 

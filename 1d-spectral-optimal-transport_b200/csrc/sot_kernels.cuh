@@ -461,7 +461,10 @@ constexpr int min_ctas(int tpf, int e, int smem_bytes, int out) {
 #ifndef SOT_REGS_LOSS_E17
 #define SOT_REGS_LOSS_E17 64
 #endif
-    const int regs = out == OUT_GRAD ? (e <= 9 ? 64 : (e <= 17 ? SOT_REGS_GRAD_E17 : 168))
+#ifndef SOT_REGS_GRAD_E9
+#define SOT_REGS_GRAD_E9 128  // one warp per frame (n_fft 512): 64 -> 128 registers = no spills, +11 % (profiles/r02_tuning.txt)
+#endif
+    const int regs = out == OUT_GRAD ? (e <= 9 ? (tpf == 32 ? SOT_REGS_GRAD_E9 : 64) : (e <= 17 ? SOT_REGS_GRAD_E17 : 168))
                                      : (e <= 9 ? 40 : (e <= 17 ? SOT_REGS_LOSS_E17 : 128));
     const int by_regs = 65536 / (tpf * regs);
     const int c = by_smem < by_regs ? by_smem : by_regs;
@@ -496,7 +499,7 @@ using IC = std::integral_constant<int, N>;
 
 // Called by one thread per CTA after its atomicAdd into *loss_sum: the CTA that draws the last ticket owns the
 // total (every other CTA's add is ordered before its ticket by the fence) and finishes the mean -- see FrameArgs.
-// Mailbox layout = sot_p2p.cu: slot [rank][phase = seq & 1] of kP2PSlot = 9 doubles, entry [8] = sequence number.
+// Mailbox layout = sot_p2p.cu: slot [rank][phase = seq & 3] of kP2PSlot = 9 doubles, entry [8] = sequence number.
 SOT_DEVINL void finish_mean(const FrameArgs& args) {
     __threadfence();
     if (atomicAdd(args.ticket, 1u) != gridDim.x - 1) return;
@@ -515,16 +518,16 @@ SOT_DEVINL void finish_mean(const FrameArgs& args) {
             seq = *args.post_seq_dev + 1ULL;
             *args.post_seq_dev = seq;
         }
-        const int phase = static_cast<int>(seq & 1ULL);
+        const int phase = static_cast<int>(seq & 3ULL);
         for (int r = 0; r < args.post_world; ++r) {
-            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 2 + phase) * 9;
+            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 4 + phase) * 9;
             asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(total) : "memory");
             asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + 1), "d"(args.post_count) : "memory");
         }
         __threadfence_system();
         const double seq_val = static_cast<double>(seq);
         for (int r = 0; r < args.post_world; ++r) {
-            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 2 + phase) * 9;
+            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 4 + phase) * 9;
             asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + 8), "d"(seq_val) : "memory");
         }
     }
@@ -818,10 +821,14 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         if constexpr (WITH_GRAD && FROM_BINS) {
             // the gradient stage sums dL/dCDF over all E entries of every thread without guards: zero what lies
             // past the end of the rows (the walk only writes real entries)
-            if (!in_u)
-                for (int idx = max(n, e0); idx < e0 + E; ++idx) sts32o<LY::G_OFF>(A0 + 4 * idx, 0.0f);
-            if (!in_v)
-                for (int idx = max(m, e0); idx < e0 + E; ++idx) sts32o<LY::G_OFF>(B0 + 4 * idx, 0.0f);
+            // (unrolled, predicated: only the warp that holds the ends of the rows takes the branch at all)
+            if (!in_u || !in_v) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) {
+                    if (e0 + c >= n) sts32o<LY::G_OFF>(A0 + 4 * (e0 + c), 0.0f);
+                    if (e0 + c >= m) sts32o<LY::G_OFF>(B0 + 4 * (e0 + c), 0.0f);
+                }
+            }
         }
 
         uint32_t adrA[NCH], adrB[NCH];

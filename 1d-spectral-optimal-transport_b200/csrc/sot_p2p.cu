@@ -7,10 +7,13 @@
 // The stores can also be made by the SOT launch itself (its last CTA, `finish_mean` in sot_kernels.cuh: the compute
 // kernel starts the exchange the moment its sum is complete) and collected by the wait-only form of this kernel.
 //
-// Mailbox (one per rank, symmetric allocation, peers mapped): [world][2 phases][kMaxVals + 1] doubles; entry
+// Mailbox (one per rank, symmetric allocation, peers mapped): [world][4 phases][kMaxVals + 1] doubles; entry
 // [r][ph][kMaxVals] is the sequence number rank r wrote last into phase ph.  Call number `seq` (1, 2, ...) uses
-// phase seq & 1: a rank can only start call seq + 2 (same phase) after every peer has written call seq + 1, i.e.
-// after every peer has finished reading call seq -- so two phases are enough.
+// phase seq & 3.  When one kernel posts and collects (in stream), a rank can only start call seq + 2 after every
+// peer has written call seq + 1, i.e. after every peer has finished reading call seq: two phases would do.  When
+// the SOT launch posts and a side stream collects, the caller lets a rank post call s only after it has COLLECTED
+// call s - 2 (`sharding.MeanExchange`): then every peer has posted s - 2, hence collected s - 4 -- the slot that
+// call s overwrites.  Four phases.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -23,6 +26,7 @@ namespace sot {
 constexpr int kP2PMaxWorld = 16;
 constexpr int kP2PMaxVals = 8;
 constexpr int kP2PSlot = kP2PMaxVals + 1;  // doubles per (rank, phase)
+constexpr int kP2PPhases = 4;
 
 struct P2PArgs {
     double* mailbox[kP2PMaxWorld];  // mailbox[r] = rank r's mailbox as mapped into this process
@@ -53,7 +57,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) {
     const int t = threadIdx.x;
     const unsigned long long seq = a.seq_dev != nullptr ? *a.seq_dev + 1ULL : a.seq;
-    const int phase = static_cast<int>(seq & 1ULL);
+    const int phase = static_cast<int>(seq & (kP2PPhases - 1));
     const double seq_val = static_cast<double>(seq);
     __shared__ int failed;
     if (t == 0) failed = 0;
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) 
     if (t < a.world) {
         if (a.post) {
             // my values, then my sequence number, into slot [rank][phase] of peer t's mailbox
-            double* dst = a.mailbox[t] + (static_cast<long long>(a.rank) * 2 + phase) * kP2PSlot;
+            double* dst = a.mailbox[t] + (static_cast<long long>(a.rank) * kP2PPhases + phase) * kP2PSlot;
             for (int i = 0; i < a.count; ++i) {
                 const double v = (a.mean_out != nullptr && i == 1) ? a.local_count : a.in[i];
                 asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + i), "d"(v) : "memory");
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) 
             asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + kP2PMaxVals), "d"(seq_val) : "memory");
         }
         // wait for rank t's contribution in my own mailbox
-        const double* src = a.mailbox[a.rank] + (static_cast<long long>(t) * 2 + phase) * kP2PSlot;
+        const double* src = a.mailbox[a.rank] + (static_cast<long long>(t) * kP2PPhases + phase) * kP2PSlot;
         const unsigned long long t0 = global_ns();
         double seen;
         do {
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(32) sot_p2p_allreduce_kernel(const P2PArgs a) 
             double v;
             asm volatile("ld.relaxed.sys.global.f64 %0, [%1];"
                          : "=d"(v)
-                         : "l"(a.mailbox[a.rank] + (static_cast<long long>(r) * 2 + phase) * kP2PSlot + t)
+                         : "l"(a.mailbox[a.rank] + (static_cast<long long>(r) * kP2PPhases + phase) * kP2PSlot + t)
                          : "memory");
             s += v;
         }
@@ -124,7 +128,7 @@ extern "C" {
 int sot_mss_launch_count_add(void);
 int sot_mss_fail(int code, const char* msg);
 
-int sot_p2p_mailbox_doubles(int32_t world) { return world * 2 * sot::kP2PSlot; }
+int sot_p2p_mailbox_doubles(int32_t world) { return world * sot::kP2PPhases * sot::kP2PSlot; }
 
 static int p2p_launch(sot::P2PArgs& a, void* const* mailboxes, int32_t world, int32_t rank, uint64_t seq, void* stream);
 

@@ -42,6 +42,8 @@ class PeerReducer:
         # call numbers kept on the device for the launches that post / collect themselves (`MeanExchange`):
         # [0] = posts made by the SOT launch, [1] = collections -- a CUDA graph of the step can be replayed
         self.seq_dev = torch.zeros(2, dtype=torch.int64, device=device)
+        self.seq_post, self.seq_wait = self.seq_dev[0:1], self.seq_dev[1:2]
+        self.ptr_array = _capi.mailbox_array(self.ptrs)  # (built once: the per-step host time matters)
         torch.cuda.synchronize(device)
         dist.barrier(self.group)  # every mailbox is zeroed before anybody writes into it
 
@@ -113,7 +115,7 @@ class MeanExchange:
     def __init__(self, process_group=None, collective="auto", overlap=False, equal_shards=True):
         self.group, self.collective, self.overlap, self.equal_shards = process_group, collective, overlap, equal_shards
         self.collective_used, self.fallback_reason = None, None
-        self._reducer, self._side, self._status = None, None, None
+        self._reducer, self._side, self._status, self._flag, self._events = None, None, None, None, None
         self._done = {}  # seq -> event: "the exchange of call seq has been collected on this rank"
         self._seq = 0
 
@@ -127,6 +129,7 @@ class MeanExchange:
         backend = dist.get_backend(self.group)
         if device.type != "cuda" or backend != "nccl":
             self.collective_used = backend  # gloo on CPU tensors: the CPU tests of this logic
+            self._status = torch.zeros(1, dtype=torch.int32)
             return
         if self.collective in ("auto", "p2p"):
             try:
@@ -143,10 +146,16 @@ class MeanExchange:
         if self.overlap:
             self._side = torch.cuda.Stream(device)
         self._status = torch.zeros(1, dtype=torch.int32).pin_memory()  # written by the device, read by the host
+        self._events = [torch.cuda.Event() for _ in range(8)]  # rotated: "SOT launch s queued" / "exchange s collected"
 
     def _check_status(self):
-        if self._status is not None and int(self._status[0]) != 0:
-            code = int(self._status[0])
+        if self._status is None:
+            return
+        if self._flag is None:
+            import ctypes
+            self._flag = ctypes.c_int32.from_address(self._status.data_ptr())  # (a plain host read, no tensor op)
+        if self._flag.value != 0:
+            code = int(self._flag.value)
             raise RuntimeError(
                 "sot_b200: the ranks of the previous step did not hold the same number of frames, so its gradients "
                 "were scaled with the wrong 1/N_global (construct with equal_shards=False)" if code == 1 else
@@ -165,11 +174,11 @@ class MeanExchange:
     def launch_kwargs(self, n_local: int, device) -> dict:
         self._seq += 1
         if device.type == "cuda" and self.overlap and (self._seq - 2) in self._done:
-            # bounded run-ahead; also what makes the two-phase mailboxes safe: a rank that posts call s has
-            # collected call s-2, hence every rank that posted s has read everything up to s-2
+            # bounded run-ahead; also what makes the four-phase mailboxes safe: a rank that posts call s has
+            # collected call s-2, so every peer has posted s-2 and therefore collected s-4 -- the slot s overwrites
             torch.cuda.current_stream(device).wait_event(self._done.pop(self._seq - 2))
         if self.collective_used == "p2p":
-            return dict(post=(self._reducer.ptrs, self._reducer.rank, self._reducer.seq_dev[0:1]),
+            return dict(post=(self._reducer.ptr_array, self._reducer.rank, self._reducer.seq_post),
                         count_value=float(n_local))
         return dict(total_out=torch.empty(2, dtype=torch.float64, device=device), count_value=float(n_local))
 
@@ -177,27 +186,32 @@ class MeanExchange:
         cuda = device.type == "cuda"
         side = self._side if (cuda and self.overlap) else None
         if side is not None:
-            side.wait_stream(torch.cuda.current_stream(device))
-        ctx = torch.cuda.stream(side) if side is not None else _NullContext()
-        with ctx:
-            if self.collective_used == "p2p":
-                mean = _capi.p2p_wait_mean(self._reducer.ptrs, self._reducer.rank, self._reducer.seq_dev[1:2],
-                                           expected_count=n_global,
-                                           status_ptr=self._status.data_ptr(), device=device)
-            else:
+            queued = self._events[(2 * self._seq) % 8]
+            queued.record()  # (on the current stream: the SOT launch of this step is queued)
+            side.wait_event(queued)
+        if self.collective_used == "p2p":
+            mean = torch.empty((), dtype=torch.float32, device=device)
+            if side is not None:
+                mean.record_stream(side)
+            _capi.p2p_wait_mean(self._reducer.ptr_array, self._reducer.rank, self._reducer.seq_wait,
+                                expected_count=n_global, status_ptr=self._status.data_ptr(), device=device,
+                                stream=side, out=mean)
+        else:
+            with (torch.cuda.stream(side) if side is not None else _NullContext()):
                 stats = kw["total_out"]
                 if side is not None:
                     stats.record_stream(side)
                 dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
                 mean = torch.where(stats[1] == n_global, stats[0] / stats[1], float("nan")).to(torch.float32)
+                # (the count check reaches the host like the peer-memory kernel's: a flag in pinned memory)
+                self._status.copy_((stats[1:2] != n_global).to(torch.int32), non_blocking=True)
             if side is not None:
-                done = torch.cuda.Event()
-                done.record()
-                self._done[self._seq] = done
-                self._done.pop(self._seq - 3, None)
+                mean.record_stream(torch.cuda.current_stream(device))
         if side is not None:
-            mean.record_stream(torch.cuda.current_stream(device))
-            mean._sot_ready = self._done[self._seq]
+            done = self._events[(2 * self._seq + 1) % 8]
+            done.record(side)
+            self._done[self._seq] = done
+            self._done.pop(self._seq - 3, None)
         return mean
 
 

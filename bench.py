@@ -262,15 +262,26 @@ def main():
     if args.mode:
         kw["backward_mode"] = args.mode
     overlap = world > 1 and not args.no_overlap and not args.graph
+    if args.graph and world > 1 and args.collective != "p2p":
+        # the captured step carries the peer-memory exchange (its call numbers live on the device, so the graph can
+        # be replayed); an NCCL all-reduce inside the captured step is not supported here
+        args.collective = "p2p"
     loss_fn = sharding.ShardedWasserstein1D(collective=args.collective, overlap_exchange=overlap, **kw)
     leaves = [(a.clone().requires_grad_(True), b.clone().requires_grad_(True)) for a, b in sets]
+
+    host_s = [0.0, 0.0, 0]  # host seconds spent issuing the forward calls / the backward calls, number of steps
 
     def eager_step(k):
         xg, yg = leaves[k % n_sets]
         xg.grad = None
         yg.grad = None
+        t0 = time.perf_counter()
         value = loss_fn(xg, yg, x_pos=pos, y_pos=pos_y)
+        t1 = time.perf_counter()
         value.backward()
+        host_s[0] += t1 - t0
+        host_s[1] += time.perf_counter() - t1
+        host_s[2] += 1
         return value
 
     graphs = None
@@ -309,6 +320,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = _capi.launch_count()
+    host_s[:] = [0.0, 0.0, 0]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` sees exactly the timed steps
     ev0.record()
@@ -319,10 +331,17 @@ def main():
     barrier()
     torch.cuda.cudart().cudaProfilerStop()
     launches = _capi.launch_count() - launches0
+    host_issue = None if host_s[2] == 0 else {"forward_us": 1e6 * host_s[0] / host_s[2],
+                                              "backward_us": 1e6 * host_s[1] / host_s[2],
+                                              "note": "host time to ISSUE one step (no synchronisation)"}
     if graphs is not None:
         launches = 2 * args.steps  # replayed from the graph: the SOT launch + the in-place scale per step
     ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    ms_by_rank = [ms_total.item() / args.steps]
     if world > 1:
+        every = [torch.zeros_like(ms_total) for _ in range(world)]
+        dist.all_gather(every, ms_total)
+        ms_by_rank = [t.item() / args.steps for t in every]
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_step = ms_total.item() / args.steps
     frames_s = frames * world / (ms_step * 1e-3)
@@ -472,11 +491,13 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": frames_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_step_by_rank": ms_by_rank,
+                "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": sampler.summary(), "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
                 "cpu_baseline": cb, "ref_on_cuda": ref_cuda, "collective": collective,
                 "collective_used": collective["used"], "value_check": value_check, "step_modes": other,
+                "host_issue": host_issue,
                 "loss": value_last, "backward_mode": loss_fn.backward_mode}
         print(json.dumps(line))
     if world > 1:

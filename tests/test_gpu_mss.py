@@ -100,19 +100,35 @@ def test_metrics_wasserstein_distance(p):
     assert abs(value.item() - g["value"].item()) <= 1e-5 * abs(g["value"].item())
 
 
-def test_training_step_example_reduces_the_loss():
-    """examples/train_step.py (reduced): the paper's loss mix inside a plain training loop."""
+def _run_example(*extra):
     import json
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "examples", "train_step.py"), "--steps", "60", "--batch", "32",
-                          "--lr", "1e-3"],
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "train_step.py"), *extra],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
-    line = json.loads(out.stdout.strip().splitlines()[-1])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def test_training_step_example_reduces_the_loss():
+    """examples/train_step.py: the paper's loss mix inside a plain training loop."""
+    line = _run_example("--steps", "60", "--batch", "32", "--lr", "1e-3", "--model", "standin")
     assert line["last_loss"] < line["first_loss"] and line["frames_per_s"] > 0
+
+
+def test_training_step_example_with_the_references_encoder_and_synth():
+    """The same step around the reference's own PESTO encoder (46 012 parameters) and DDSP oscillator bank, imported
+    unmodified from the staged copy baseline/_ref/ (git-ignored; made by `__graft_entry__.build()`)."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not (os.path.isfile("/root/reference/encoder.py") or os.path.isfile(os.path.join(root, "baseline", "_ref", "encoder.py"))):
+        pytest.skip("the reference's files are not staged on this box")
+    line = _run_example("--steps", "40", "--batch", "32", "--lr", "1e-3", "--model", "reference", "--loss-share")
+    assert line["model"] == "reference" and line["trainable_parameters"] == 46012
+    assert line["last_loss"] == line["last_loss"] and line["last_loss"] < line["first_loss"]  # finite and going down
+    assert 0.0 <= line["loss_share"]["share_of_step_in_the_two_losses"] <= 1.0
 
 
 def test_peer_memory_all_reduce_matches_nccl():
@@ -131,3 +147,6 @@ def test_peer_memory_all_reduce_matches_nccl():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["values_match_nccl"] is True
+    # the fused sharded path bench.py runs: value vs one GPU over all shards, gradients vs single-GPU gradients, with
+    # every exchange; graph replay; unequal shards caught
+    assert line["sharded_loss_ok"] and line["graph_replay_ok"] and line["unequal_shards_ok"] and line["all_ok"], line
