@@ -43,8 +43,8 @@ L2_BYTES = 126e6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sot2048-nocut-sweep", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=65536, help="frames per GPU (weak) or in total (strong)")
@@ -72,34 +72,57 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML every ~2 ms (the timed region of a
+    0.4 ms step is only tens of milliseconds long), `nvidia-smi` every 200 ms if NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.sm_max, self.source, self.nvml, self.handle = None, "nvidia-smi", None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
+                if self.nvml is not None:
+                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.samples.append((mhz, mask))
+                    self.stop_flag.wait(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
+                    self.sm_max = float(parts[1])
+                    mask = sum(bit for k, (_, bit) in enumerate(self.BITS) if parts[2 + k].lower().startswith("active"))
+                    self.samples.append((float(parts[0]), mask))
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [name for name, bit in self.BITS if any(s[1] & bit for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm),
+                "source": self.source}
 
 
 def positions(n_fft, grid):
@@ -107,7 +130,7 @@ def positions(n_fft, grid):
     return S.linear_positions(n_fft) if grid == "linear" else S.logf_positions(n_fft)
 
 
-def cpu_reference_leg(n_fft, cut, grid, total_frames, chunk_frames, steps, warmup, seconds_cap=None):
+def cpu_reference_leg(n_fft, cut, grid, total_frames, chunk_frames, steps, warmup, seconds_cap=None, budget_s=None):
     """The reference's CPU implementation timed on this box's host cores, forward + backward, both gradients: the
     UNMODIFIED `losses.Wasserstein1D` when its files are present (`/root/reference`, or the verbatim git-ignored
     copy under baseline/_ref/ that travels to the GPU box: kind "reference"), else the oracle port, which is pinned
@@ -135,6 +158,15 @@ def cpu_reference_leg(n_fft, cut, grid, total_frames, chunk_frames, steps, warmu
 
     per_call = x.shape[0] * x.shape[1]
     calls = max(1, -(-total_frames // per_call))
+    if budget_s is not None:
+        # bounded sample: as many calls per step as fit `budget_s` seconds for the whole run (one probe call sets the rate)
+        xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        call(xr, yr).backward()
+        t0 = time.perf_counter()
+        xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        call(xr, yr).backward()
+        per_call_s = time.perf_counter() - t0
+        calls = max(1, min(calls, int(budget_s / (per_call_s * (steps + warmup)))))
 
     def step():
         for _ in range(calls):
@@ -155,6 +187,7 @@ def cpu_reference_leg(n_fft, cut, grid, total_frames, chunk_frames, steps, warmu
     n = per_call * calls
     total = sum(times)
     return {"value": n * len(times) / total, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind,
+            "frames_per_step": n,
             "sample": f"{len(times)} steps x {n} frames x {x.shape[-1]} bins in calls of {per_call} frames ({what}; "
                       f"torch CPU ops, fwd+bwd, both grads), median {sorted(times)[len(times) // 2] * 1e3:.1f} ms/step"
             }, total / len(times)
@@ -223,12 +256,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        config["cpu_chunk_frames"] = args.cpu_frames
-        cb, ms = cpu_reference_leg(n_fft, cut, grid, frames * world, args.cpu_frames, args.steps, max(args.warmup, 1))
+        cb, ms = cpu_reference_leg(n_fft, cut, grid, frames * world, args.cpu_frames, args.steps, max(args.warmup, 1),
+                                   budget_s=150.0)
+        sample = {"frames_per_step": cb["frames_per_step"], "frames_per_call": args.cpu_frames,
+                  "what": ("the whole workload every step" if cb["frames_per_step"] >= frames * world else
+                           "a bounded sample of the workload every step (the run is sized to ~150 s)")}
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3,
                           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": config, "cpu_baseline": cb, "gpu_launches": 0,
+                          "data": "synthetic", "config": config, "reference_sample": sample, "cpu_baseline": cb,
+                          "gpu_launches": 0,
                           "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
                                   "d2h_bytes_per_step": 0}}))
         return
