@@ -499,7 +499,7 @@ using IC = std::integral_constant<int, N>;
 
 // Called by one thread per CTA after its atomicAdd into *loss_sum: the CTA that draws the last ticket owns the
 // total (every other CTA's add is ordered before its ticket by the fence) and finishes the mean -- see FrameArgs.
-// Mailbox layout = sot_p2p.cu: slot [rank][phase = seq & 3] of kP2PSlot = 9 doubles, entry [8] = sequence number.
+// Mailbox layout = sot_p2p.cu: slot [rank][phase = seq & 7] of kP2PSlot = 9 doubles, entry [8] = sequence number.
 SOT_DEVINL void finish_mean(const FrameArgs& args) {
     __threadfence();
     if (atomicAdd(args.ticket, 1u) != gridDim.x - 1) return;
@@ -518,16 +518,16 @@ SOT_DEVINL void finish_mean(const FrameArgs& args) {
             seq = *args.post_seq_dev + 1ULL;
             *args.post_seq_dev = seq;
         }
-        const int phase = static_cast<int>(seq & 3ULL);
+        const int phase = static_cast<int>(seq & 7ULL);
         for (int r = 0; r < args.post_world; ++r) {
-            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 4 + phase) * 9;
+            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 8 + phase) * 9;
             asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(total) : "memory");
             asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + 1), "d"(args.post_count) : "memory");
         }
-        __threadfence_system();
+        // (the release store orders this thread's own stores above before the sequence number: no separate fence)
         const double seq_val = static_cast<double>(seq);
         for (int r = 0; r < args.post_world; ++r) {
-            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 4 + phase) * 9;
+            double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 8 + phase) * 9;
             asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + 8), "d"(seq_val) : "memory");
         }
     }

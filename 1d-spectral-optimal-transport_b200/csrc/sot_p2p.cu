@@ -7,13 +7,13 @@
 // The stores can also be made by the SOT launch itself (its last CTA, `finish_mean` in sot_kernels.cuh: the compute
 // kernel starts the exchange the moment its sum is complete) and collected by the wait-only form of this kernel.
 //
-// Mailbox (one per rank, symmetric allocation, peers mapped): [world][4 phases][kMaxVals + 1] doubles; entry
+// Mailbox (one per rank, symmetric allocation, peers mapped): [world][8 phases][kMaxVals + 1] doubles; entry
 // [r][ph][kMaxVals] is the sequence number rank r wrote last into phase ph.  Call number `seq` (1, 2, ...) uses
-// phase seq & 3.  When one kernel posts and collects (in stream), a rank can only start call seq + 2 after every
+// phase seq & 7.  When one kernel posts and collects (in stream), a rank can only start call seq + 2 after every
 // peer has written call seq + 1, i.e. after every peer has finished reading call seq: two phases would do.  When
 // the SOT launch posts and a side stream collects, the caller lets a rank post call s only after it has COLLECTED
-// call s - 2 (`sharding.MeanExchange`): then every peer has posted s - 2, hence collected s - 4 -- the slot that
-// call s overwrites.  Four phases.
+// call s - 4 (`sharding.MeanExchange`: the ranks may drift four steps apart): then every peer has posted s - 4,
+// hence collected s - 8 -- the slot that call s overwrites.  Eight phases.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -26,7 +26,7 @@ namespace sot {
 constexpr int kP2PMaxWorld = 16;
 constexpr int kP2PMaxVals = 8;
 constexpr int kP2PSlot = kP2PMaxVals + 1;  // doubles per (rank, phase)
-constexpr int kP2PPhases = 4;
+constexpr int kP2PPhases = 8;
 
 struct P2PArgs {
     double* mailbox[kP2PMaxWorld];  // mailbox[r] = rank r's mailbox as mapped into this process

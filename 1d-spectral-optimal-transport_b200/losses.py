@@ -85,10 +85,11 @@ def _rows(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise _capi.SotError(f"sot_b200: `{name}` lives on {t.device}; the SOT kernels are CUDA only "
                              "(no CPU fallback exists by design)")
-    if t.dtype in (torch.float16, torch.bfloat16):
-        t = t.float()
+    if t.dtype in (torch.float16, torch.bfloat16, torch.float64):
+        t = t.float()  # (float64: the reference accepts it; the kernels compute in float32, the result is cast back)
     elif t.dtype not in (torch.float32, torch.complex64):
-        raise TypeError(f"sot_b200: `{name}` must be float32 (or half/bfloat16, upcast) or complex64, got {t.dtype}")
+        raise TypeError(f"sot_b200: `{name}` must be float32 (half / bfloat16 / float64 are converted) or complex64, "
+                        f"got {t.dtype}")
     if t.ndim == 3:
         t = t.reshape(-1, t.shape[-1])
     elif t.ndim != 2:
@@ -342,17 +343,21 @@ class Wasserstein1D(torch.nn.Module):
             return [t.reshape(original_shape + (-1,)) for t in out]  # losses.py:198-201
 
         mode = getattr(self, "backward_mode", DEFAULT_BACKWARD_MODE)
+        as64 = x.dtype == torch.float64 or y.dtype == torch.float64  # the reference returns float64 then
         if not self.hinge and kwargs.get("dims", None) is None and x.numel() > 0:
             # plain mean over all frames (every paper config): folded into the one kernel launch
-            return sot_mean(x, y, x_pos_, y_pos_, p=self.p, square=bool(self.square_dist), cut_scale=cut_scale,
-                            limit=limit, require_sort=need_sort, exchange=self._mean_exchange(),
-                            backward_mode="recompute" if mode == "recompute" else "onepass")
+            value = sot_mean(x, y, x_pos_, y_pos_, p=self.p, square=bool(self.square_dist), cut_scale=cut_scale,
+                             limit=limit, require_sort=need_sort, exchange=self._mean_exchange(),
+                             backward_mode="recompute" if mode == "recompute" else "onepass")
+            return value.double() if as64 else value
         loss = sot_frames(x, y, x_pos_, y_pos_, p=self.p, square=bool(self.square_dist), cut_scale=cut_scale,
                           limit=limit, require_sort=need_sort,
                           backward_mode="recompute" if mode == "recompute" else "fused")
         if self.hinge:  # losses.py:203-205: the ctor flag gates, the call kwarg is the threshold
             loss = torch.nn.functional.relu(loss - kwargs.get("hinge", 0.0))
         loss = loss.reshape(original_shape)
+        if as64:
+            loss = loss.double()
         return torch.mean(loss, dim=kwargs.get("dims", None))  # losses.py:211
 
 

@@ -64,8 +64,32 @@ def mss_term(zt, zv, mag_weight=1.0, logmag_weight=0.0, loss_type="L1") -> torch
     return _MssTerm.apply(zt, zv, mag_weight, logmag_weight, _capi.SOT_MSS_L1 if kind == "L1" else _capi.SOT_MSS_L2)
 
 
+def _partial_mean_term(zt, zv, mag_weight, logmag_weight, loss_type, dims):
+    """`mean_difference(..., dims=dims)` (losses.py:7-36) for a caller that wants per-item values (evaluation):
+    a partial mean has no single scalar to reduce into, so this rarely used form runs as torch reductions on the
+    magnitudes, like the reference; the training form (dims=None) is the fused kernel pair."""
+    kind = loss_type.upper()
+    if kind not in ("L1", "L2"):
+        raise ValueError('Loss type ({}), must be "L1", "L2" '.format(kind))  # losses.py:36
+    tm, vm = zt.abs().float(), zv.abs().float()
+
+    def mean_difference(a, b):
+        d = a - b
+        return torch.mean(d.abs() if kind == "L1" else d ** 2, dim=dims)
+
+    out = 0.0
+    if mag_weight > 0:
+        out = out + mag_weight * mean_difference(tm, vm)
+    if logmag_weight > 0:
+        eps = torch.tensor(1e-5, device=tm.device)  # utils.py:145-151 `safe_log`
+        out = out + logmag_weight * mean_difference(torch.log(torch.where(tm <= eps, eps, tm)),
+                                                    torch.log(torch.where(vm <= eps, eps, vm)))
+    return out
+
+
 class MSSLoss(torch.nn.Module):
-    """losses.py:365-425.  `dims` (a partial mean) is not on the fused path and is refused."""
+    """losses.py:365-425.  `dims=None` (every training config): one fused reduction kernel and one gradient kernel
+    per FFT size; `dims=...` (a partial mean): torch reductions on the magnitudes, like the reference."""
 
     def __init__(self, fft_sizes=(2048, 1024, 512, 256, 128, 64), loss_type="L1", mag_weight=0.0, logmag_weight=0.0):
         super().__init__()
@@ -75,15 +99,17 @@ class MSSLoss(torch.nn.Module):
         self.logmag_weight = logmag_weight
 
     def forward(self, target_audio, audio, **kwargs):
-        if kwargs.get("dims", None) is not None:
-            raise NotImplementedError("sot_b200: MSSLoss with `dims` (partial means) is not implemented")
+        dims = kwargs.get("dims", None)
         loss = 0.0
         if not (self.mag_weight > 0 or self.logmag_weight > 0):
             return loss  # the reference adds nothing either (losses.py:409, 415)
         for size in self.fft_sizes:
             zt = stft(target_audio, frame_size=size)  # compute_mag's defaults: overlap 0.75, hann, end padding
             zv = stft(audio, frame_size=size)
-            loss = loss + mss_term(zt, zv, max(self.mag_weight, 0.0), max(self.logmag_weight, 0.0), self.loss_type)
+            if dims is None:
+                loss = loss + mss_term(zt, zv, max(self.mag_weight, 0.0), max(self.logmag_weight, 0.0), self.loss_type)
+            else:
+                loss = loss + _partial_mean_term(zt, zv, self.mag_weight, self.logmag_weight, self.loss_type, dims)
         return loss
 
 

@@ -15,6 +15,9 @@ import torch.distributed as dist
 from . import _capi, losses
 
 
+RUN_AHEAD = 4  # steps a rank may run ahead of the collection of its exchanges (mailbox phases = 2 * RUN_AHEAD)
+
+
 def shard_bounds(n_items: int, rank: int, world: int):
     """Contiguous, balanced split of `n_items` (signals, so a signal's frames stay together)."""
     base, extra = divmod(n_items, world)
@@ -110,7 +113,7 @@ class MeanExchange:
       (`sot_p2p_wait_mean_device`); "nccl" / "gloo" -- `torch.distributed.all_reduce` of two doubles.
     * `overlap=True` runs the collecting half on a side stream, so neither the backward nor the next step's launch
       ever waits for the slowest rank; the returned tensor is then valid on the current stream only after
-      `sharding.wait_value(loss)` (bounded run-ahead: step s waits for the exchange of step s-2)."""
+      `sharding.wait_value(loss)` (bounded run-ahead: step s waits for the exchange of step s-4)."""
 
     def __init__(self, process_group=None, collective="auto", overlap=False, equal_shards=True):
         self.group, self.collective, self.overlap, self.equal_shards = process_group, collective, overlap, equal_shards
@@ -146,7 +149,7 @@ class MeanExchange:
         if self.overlap:
             self._side = torch.cuda.Stream(device)
         self._status = torch.zeros(1, dtype=torch.int32).pin_memory()  # written by the device, read by the host
-        self._events = [torch.cuda.Event() for _ in range(8)]  # rotated: "SOT launch s queued" / "exchange s collected"
+        self._events = [torch.cuda.Event() for _ in range(4 * RUN_AHEAD)]  # rotated: "launch s queued" / "exchange s collected"
 
     def _check_status(self):
         if self._status is None:
@@ -173,10 +176,10 @@ class MeanExchange:
 
     def launch_kwargs(self, n_local: int, device) -> dict:
         self._seq += 1
-        if device.type == "cuda" and self.overlap and (self._seq - 2) in self._done:
-            # bounded run-ahead; also what makes the four-phase mailboxes safe: a rank that posts call s has
-            # collected call s-2, so every peer has posted s-2 and therefore collected s-4 -- the slot s overwrites
-            torch.cuda.current_stream(device).wait_event(self._done.pop(self._seq - 2))
+        if device.type == "cuda" and self.overlap and (self._seq - RUN_AHEAD) in self._done:
+            # bounded run-ahead; also what makes the eight-phase mailboxes safe: a rank that posts call s has
+            # collected call s-4, so every peer has posted s-4 and therefore collected s-8 -- the slot s overwrites
+            torch.cuda.current_stream(device).wait_event(self._done.pop(self._seq - RUN_AHEAD))
         if self.collective_used == "p2p":
             return dict(post=(self._reducer.ptr_array, self._reducer.rank, self._reducer.seq_post),
                         count_value=float(n_local))
@@ -186,7 +189,7 @@ class MeanExchange:
         cuda = device.type == "cuda"
         side = self._side if (cuda and self.overlap) else None
         if side is not None:
-            queued = self._events[(2 * self._seq) % 8]
+            queued = self._events[(2 * self._seq) % (4 * RUN_AHEAD)]
             queued.record()  # (on the current stream: the SOT launch of this step is queued)
             side.wait_event(queued)
         if self.collective_used == "p2p":
@@ -208,10 +211,10 @@ class MeanExchange:
             if side is not None:
                 mean.record_stream(torch.cuda.current_stream(device))
         if side is not None:
-            done = self._events[(2 * self._seq + 1) % 8]
+            done = self._events[(2 * self._seq + 1) % (4 * RUN_AHEAD)]
             done.record(side)
             self._done[self._seq] = done
-            self._done.pop(self._seq - 3, None)
+            self._done.pop(self._seq - RUN_AHEAD - 1, None)
         return mean
 
 

@@ -71,58 +71,67 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML every ~2 ms (the timed region of a
-    0.4 ms step is only tens of milliseconds long), `nvidia-smi` every 200 ms if NVML cannot be loaded."""
+class ClockSampler:
+    """SM clock and throttle reasons WHILE the timed region runs: one `nvidia-smi -lms 50` child process streams a
+    line every 50 ms, a thread only reads the pipe (it sleeps in the read; NVML calls from this process -- from a
+    polling thread or from the timing loop itself -- were measured to stall the launch path by 10 %).  The summary
+    uses the samples that fell between `begin()` and `end()`; when the region was shorter than the sampling period
+    it uses the samples of the whole loaded phase (warm-up, timed steps, kernel-alone loops) and says so."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
-        self.sm_max, self.source, self.nvml, self.handle = None, "nvidia-smi", None, None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
-            self.nvml, self.source = pynvml, "nvml"
-        except Exception:
-            self.nvml = None
+        self.index, self.samples, self.proc, self.thread = index, [], None, None
+        self.t_begin, self.t_end = None, None
 
-    def run(self):
-        while not self.stop_flag.is_set():
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
+            if len(parts) >= 6:
+                try:
+                    self.samples.append((time.perf_counter(), float(parts[0]), float(parts[1]),
+                                         tuple(p.lower().startswith("active") for p in parts[2:6])))
+                except ValueError:
+                    pass
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                if self.nvml is not None:
-                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
-                    try:
-                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                    except Exception:
-                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                    self.samples.append((mhz, mask))
-                    self.stop_flag.wait(0.002)
-                    continue
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.sm_max = float(parts[1])
-                    mask = sum(bit for k, (_, bit) in enumerate(self.BITS) if parts[2 + k].lower().startswith("active"))
-                    self.samples.append((float(parts[0]), mask))
+                self.proc.wait(timeout=5)
             except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
-        sm = sorted(s[0] for s in self.samples)
-        reasons = [name for name, bit in self.BITS if any(s[1] & bit for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm),
-                "source": self.source}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        inside = [s for s in self.samples if self.t_begin is not None and self.t_begin <= s[0] <= (self.t_end or 1e30)]
+        used = inside if inside else self.samples
+        sm = sorted(s[1] for s in used)
+        reasons = [n for k, n in enumerate(self.NAMES) if any(s[3][k] for s in used)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": used[0][2], "reasons": reasons, "samples": len(used),
+                "samples_inside_timed_region": len(inside),
+                "window": "timed region" if inside else "loaded phase around the timed region (region < 50 ms)"}
 
 
 def positions(n_fft, grid):
@@ -351,21 +360,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for k in range(max(args.warmup, 3)):
         value = step(k)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = _capi.launch_count()
     host_s[:] = [0.0, 0.0, 0]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` sees exactly the timed steps
+    if world > 1:
+        # the ranks leave the host barrier above milliseconds apart; an in-stream all-reduce lines the GPUs up again
+        # right before the first timed step (each rank's stream waits for every peer), so that the max over ranks
+        # measures the steps and not the start skew
+        dist.all_reduce(torch.zeros(1, device=dev))
     ev0.record()
+    sampler.begin()
     for k in range(args.steps):
         value = step(k)
     loss_fn.wait_value(value)  # (overlapped exchange: the last value is part of the timed region)
     ev1.record()
     barrier()
+    sampler.end()
     torch.cuda.cudart().cudaProfilerStop()
     launches = _capi.launch_count() - launches0
     host_issue = None if host_s[2] == 0 else {"forward_us": 1e6 * host_s[0] / host_s[2],
@@ -431,8 +447,7 @@ def main():
                   args.steps)
     f_avg = timed(lambda xs, ys: _capi.mean_step(xs, ys, pos, pos_y, 2.0, flags, grad_scale=inv, mean_scale=1.0 / frames,
                                                  want_gu=False, want_gv=False), args.steps)
-    sampler.stop_flag.set()
-    sampler.join()
+    sampler.stop()
     peak, peak_src = peaks()
     bytes_fused = (16 * F + 4) * frames  # reads u, v; writes grad_u, grad_v (+ the frame's share of the sum)
     bytes_fwd = (8 * F + 4) * frames     # reads u, v

@@ -92,6 +92,27 @@ def test_mss_only_prediction_needs_grad_and_misuse(MSS):
     assert set(out) == {"MSSLoss"} and out["MSSLoss"].item() > 0
 
 
+def test_mss_partial_means_like_the_reference(MSS):
+    """`MSSLoss(...)(x, y, dims=...)` (losses.py:409-421 via `mean_difference(dims=)`): per-item values."""
+    from oracle import mss_oracle as MO
+    gen = torch.Generator().manual_seed(11)
+    a, b = torch.randn(3, 4096, generator=gen) * 0.1, torch.randn(3, 4096, generator=gen) * 0.1
+    mod = MSS.MSSLoss(fft_sizes=(512, 128), mag_weight=1.0, logmag_weight=0.5, loss_type="L2")
+    bd = b.to(DEV).requires_grad_(True)
+    got = mod(a.to(DEV), bd, dims=(1, 2))
+    assert got.shape == (3,)
+    want = 0.0
+    for size in (512, 128):
+        tm, vm = MO.magnitude_frames(a, size), MO.magnitude_frames(b, size)
+        want = want + ((tm - vm) ** 2).mean(dim=(1, 2)) + 0.5 * ((MO.guarded_log(tm) - MO.guarded_log(vm)) ** 2).mean(dim=(1, 2))
+    assert torch.allclose(got.detach().cpu(), want, rtol=2e-4, atol=1e-7)
+    got.sum().backward()
+    assert bd.grad is not None and torch.isfinite(bd.grad).all()
+    # and the full mean of the per-item values is the fused scalar
+    full = mod(a.to(DEV), b.to(DEV))
+    assert abs(full.item() - got.mean().item()) <= 1e-4 * abs(full.item())
+
+
 @pytest.mark.parametrize("p", [1, 2])
 def test_metrics_wasserstein_distance(p):
     from sot_b200 import metrics

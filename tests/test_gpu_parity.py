@@ -499,6 +499,21 @@ def test_hinge_gate_and_threshold(L):
         assert torch.equal(mine.reshape(30, -1).abs().sum(1) == 0, ref.reshape(30, -1).abs().sum(1) == 0), "hinge gate"
 
 
+def test_float64_inputs_are_accepted_like_the_reference(L):
+    """The reference (and its `ref64` evaluation) takes float64 spectra: the drop-in converts, computes in float32
+    and hands float64 values and gradients back."""
+    g = G.load("sot512_nocut")
+    ctor = dict(g["meta"]["ctor"])
+    x = g["x"].double().to(DEV).requires_grad_(True)
+    y = g["y"].double().to(DEV).requires_grad_(True)
+    v = L.Wasserstein1D(**ctor)(x, y, x_pos=g["pos_x"].double().to(DEV), y_pos=g["pos_y"].double().to(DEV))
+    v.backward()
+    assert v.dtype == torch.float64 and x.grad.dtype == torch.float64 and y.grad.dtype == torch.float64
+    assert abs(v.item() - g["value"].item()) <= 1e-5 * abs(g["value"].item())
+    rows = L.Wasserstein1D(**ctor)(x.detach(), y.detach(), x_pos=g["pos_x"].to(DEV), y_pos=g["pos_y"].to(DEV), dims=1)
+    assert rows.dtype == torch.float64 and rows.shape == g["x"].shape[:1]
+
+
 @pytest.mark.parametrize("p,limit", [(1, False), (2, True)])
 def test_module_level_w1d_unequal_unsorted_supports(L, p, limit):
     g = G.load(f"w1d_n37_m90_p{p}")
