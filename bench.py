@@ -431,17 +431,18 @@ def main():
     inv = 1.0 / (frames * world)
 
     def timed(fn, reps):
-        out = []
-        for it in range(3 + reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            xs, ys = sets[it % n_sets]
-            a.record()
-            fn(xs, ys)
-            b.record()
-            b.synchronize()
-            if it >= 3:
-                out.append(a.elapsed_time(b))
-        return sum(out) / len(out)
+        """Average duration of `reps` back-to-back launches, CUDA events on the launching stream (one pair around
+        the whole train: an event pair per launch would add the launch latency of a ~0.4 ms kernel to each)."""
+        for it in range(3):
+            fn(*sets[it % n_sets])
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for it in range(reps):
+            fn(*sets[it % n_sets])
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps
 
     k_avg = timed(lambda xs, ys: _capi.mean_step(xs, ys, pos, pos_y, 2.0, flags, grad_scale=inv, mean_scale=1.0 / frames),
                   args.steps)

@@ -640,7 +640,7 @@ def test_inputs_are_not_modified_and_wrong_dtype_raises(capi, L):
     capi.forward_backward(x, y, pos, pos, 2.0, capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT)
     assert torch.equal(x, x0) and torch.equal(y, y0)
     with pytest.raises(TypeError):
-        L.Wasserstein1D(p=2, fixed_x=65)(x.double(), y.double())
+        L.Wasserstein1D(p=2, fixed_x=65)(x.long(), y.long())  # (float64 is converted like the reference accepts it)
     half = L.Wasserstein1D(p=2, fixed_x=65).to(DEV)(x.half(), y.half())
     assert torch.isfinite(half)
 
