@@ -524,11 +524,13 @@ SOT_DEVINL void finish_mean(const FrameArgs& args) {
             asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(total) : "memory");
             asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + 1), "d"(args.post_count) : "memory");
         }
-        // (the release store orders this thread's own stores above before the sequence number: no separate fence)
+        // ONE system-scope fence between the values and the sequence numbers of all peers (a release store per peer
+        // is a fence per peer: measured 21 us per step at 8 GPUs against 10 us at 2), then plain stores
+        __threadfence_system();
         const double seq_val = static_cast<double>(seq);
         for (int r = 0; r < args.post_world; ++r) {
             double* dst = args.post_mailbox[r] + (static_cast<long long>(args.post_rank) * 8 + phase) * 9;
-            asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(dst + 8), "d"(seq_val) : "memory");
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + 8), "d"(seq_val) : "memory");
         }
     }
 }
