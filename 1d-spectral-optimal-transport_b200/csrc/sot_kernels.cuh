@@ -456,7 +456,7 @@ SOT_DEVINL void cta_scan2d(double& a, double& b, double& total_a, double& total_
 constexpr int min_ctas(int tpf, int e, int smem_bytes, int out) {
     const int by_smem = (227 * 1024) / (smem_bytes + 1024);
 #ifndef SOT_REGS_GRAD_E17  // (tuning experiments: -DSOT_REGS_GRAD_E17=.. -DSOT_REGS_LOSS_E17=..)
-#define SOT_REGS_GRAD_E17 128
+#define SOT_REGS_GRAD_E17 96
 #endif
 #ifndef SOT_REGS_LOSS_E17
 #define SOT_REGS_LOSS_E17 64
@@ -1140,21 +1140,29 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 // barrier carries the suffix scan, these sums and the loss.  Nothing is read back from the CDF rows
                 // (their past-the-end entries are +inf) and their shared-memory traffic is gone.
                 // (packed fp32 on (u, v) pairs, like the CDF stage)
-                f32x2 ls2[E];
+                // Real rows: the E local suffix sums are NOT kept (34 registers across the scan): the emit loop below
+                // reads dL/dCDF a second time and rebuilds them in the same order -- bit-identical values, +E shared-
+                // memory loads per thread, and the register file holds 10 instead of 8 frames per SM.  The first
+                // three pairs stay in registers: the emit loop of the thread before me writes its last outputs over
+                // them (output staging is in place, shifted by the destination's 16-byte phase of <= 3 floats).
+                constexpr bool KEEP_LS = CPLX;
+                constexpr int NKEEP = (E < 3) ? E : 3;
+                f32x2 ls2[KEEP_LS ? E : 1];
+                f32x2 gk[NKEEP];
                 f32x2 s2 = 0, d2 = 0;
                 const bool sqw = square && !CPLX;  // x2 holds magnitudes: w ~ x^2; else x2 is what was accumulated
+                auto suffix_pass = [&](auto SQW) {
 #pragma unroll
-                for (int c = E - 1; c >= 0; --c) {
-                    s2 = add2(s2, lds32x2(GA0 + 4 * (e0 + c), GB0 + 4 * (e0 + c)));
-                    ls2[c] = s2;
-                }
-                if (sqw) {
-#pragma unroll
-                    for (int c = 0; c < E; ++c) d2 = fma2(mul2(x2[c], x2[c]), ls2[c], d2);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < E; ++c) d2 = fma2(x2[c], ls2[c], d2);
-                }
+                    for (int c = E - 1; c >= 0; --c) {
+                        const f32x2 g2 = lds32x2(GA0 + 4 * (e0 + c), GB0 + 4 * (e0 + c));
+                        s2 = add2(s2, g2);
+                        if constexpr (KEEP_LS) ls2[c] = s2;
+                        if (c < NKEEP) gk[c] = g2;
+                        d2 = fma2(decltype(SQW)::value ? mul2(x2[c], x2[c]) : x2[c], s2, d2);
+                    }
+                };
+                if (sqw) suffix_pass(std::true_type{}); else suffix_pass(std::false_type{});
+                (void)ls2;
                 float su, sv, du, dv;
                 unpack2(s2, su, sv);
                 unpack2(d2, du, dv);
@@ -1214,9 +1222,11 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     // (uniform choice hoisted out of the element loop; all E entries are stored: what lies past the
                     // row stays in the staging row)
                     auto emit = [&](auto SQ) {
+                        f32x2 r2 = 0;  // the local suffix sums again, same order as above
 #pragma unroll
-                        for (int c = 0; c < E; ++c) {
-                            f32x2 g2 = mul2(add2(b2, ls2[c]), k2);
+                        for (int c = E - 1; c >= 0; --c) {  // (descending: what I overwrite I have read)
+                            r2 = add2(r2, c < NKEEP ? gk[c] : lds32x2(GA0 + 4 * (e0 + c), GB0 + 4 * (e0 + c)));
+                            f32x2 g2 = mul2(add2(b2, r2), k2);
                             if constexpr (decltype(SQ)::value) g2 = mul2(g2, x2[c]);
                             float ga, gb;
                             unpack2(g2, ga, gb);
