@@ -132,7 +132,12 @@ def _version(t: torch.Tensor):
 
 def _is_ascending(pos: torch.Tensor, owner: torch.Tensor) -> bool:
     """One device->host read per distinct (tensor object, version) of the caller's positions
-    tensor `owner`; cached after that (a `fixed_x` buffer or a grid the caller keeps is checked once)."""
+    tensor `owner`; cached after that (a `fixed_x` buffer or a grid the caller keeps is checked once).
+
+    Callers that build a NEW positions tensor every step (the reference's `trainer.py:187-197` does) pay this read
+    -- and the one in `_uniform_grid` -- every step: a host synchronisation with the stream.  Keep the positions
+    tensor (hoist it out of the step, as `features.Wasserstein1DWithTransform` does) and the step stays
+    synchronisation free; INTEGRATION.md says so."""
     key = id(owner)
     version = _version(owner)
     hit = _sorted_cache.get(key)
@@ -164,7 +169,8 @@ def _order(pos: torch.Tensor, w: torch.Tensor, owner: torch.Tensor):
 _uniform_cache: dict = {}  # (id(x_pos), id(y_pos)) -> (weakref, weakref, version, version, uniform?)
 
 
-def _uniform_grid(pu: torch.Tensor, pv: torch.Tensor, owner_u: torch.Tensor, owner_v: torch.Tensor) -> bool:
+def _uniform_grid(pu: torch.Tensor, pv: torch.Tensor, owner_u: torch.Tensor, owner_v: torch.Tensor,
+                  sorted_flags=(False, False)) -> bool:
     """Are both supports EXACT uniform grids pos[i] = pos[0] + i*h with one common power-of-two h, so
     that every position and every position difference is exact in float32?  True for rfftfreq / max
     with a power-of-two n_fft (trainer.py:193-197) and for `fixed_x = linspace(0, 1, 2**k + 1)`
@@ -172,7 +178,7 @@ def _uniform_grid(pu: torch.Tensor, pv: torch.Tensor, owner_u: torch.Tensor, own
     results, fewer shared-memory accesses.  One device->host read per distinct pair of caller tensors."""
     if pu.ndim != 1 or pv.ndim != 1 or pu.shape[0] < 2 or pv.shape[0] < 2:
         return False
-    key = (id(owner_u), id(owner_v))
+    key = (id(owner_u), id(owner_v), tuple(sorted_flags))  # (the verdict depends on whether a support was re-sorted)
     ver_u, ver_v = _version(owner_u), _version(owner_v)
     cacheable = ver_u is not None and ver_v is not None
     hit = _uniform_cache.get(key)
@@ -217,7 +223,7 @@ def _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_
         pv, v = _order(pv, v, y_pos)
     flags = ((_capi.SOT_SQUARE if square else 0) | (_capi.SOT_CUT_SCALE if cut_scale else 0) |
              (_capi.SOT_LIMIT if limit else 0) | (_capi.SOT_RAW_WEIGHTS if raw_weights else 0) |
-             (_capi.SOT_UNIFORM_GRID if _uniform_grid(pu, pv, x_pos, y_pos) else 0))
+             (_capi.SOT_UNIFORM_GRID if _uniform_grid(pu, pv, x_pos, y_pos, (bool(sort_u), bool(sort_v))) else 0))
     return u, v, pu, pv, flags
 
 

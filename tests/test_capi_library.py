@@ -47,6 +47,17 @@ def test_argument_validation_happens_before_any_launch():
     assert lib.sot_forward_device(ctypes.byref(prob), ctypes.c_void_p(16), None) == -1  # unknown flag
     prob = _capi.SotProblem(4, 60000, 60000, 16, 16, 16, 16, 0, 0, 2.0, 0)
     assert lib.sot_forward_device(ctypes.byref(prob), ctypes.c_void_p(16), None) == -2  # does not fit
+    # the host-buffer entry is sized for real rows: complex (STFT) rows are refused before anything is allocated
+    prob = _capi.SotProblem(4, 9, 9, 16, 16, 16, 16, 0, 0, 2.0, _capi.SOT_COMPLEX_INPUT)
+    assert lib.sot_loss_grad_host(ctypes.byref(prob), None, ctypes.c_void_p(16), None, None, 0) == -1
+    assert b"SOT_COMPLEX_INPUT" in lib.sot_last_error()
+    # the one-launch step: plan and workspace are required, peers must be described completely
+    plan = _capi.SotMeanPlan()
+    prob = _capi.SotProblem(4, 9, 9, 16, 16, 16, 16, 0, 0, 2.0, 0)
+    assert lib.sot_mean_step_device(ctypes.byref(prob), ctypes.byref(plan), None, None, None, None) == -1
+    plan.workspace, plan.post_world = 16, 3
+    assert lib.sot_mean_step_device(ctypes.byref(prob), ctypes.byref(plan), None, None, None, None) == -1
+    assert lib.sot_scale_inplace_device(ctypes.c_void_p(16), 4, None, 0, None, None) == -1
     assert lib.sot_set_tuning(48, 7, 0) == -1
     assert lib.sot_set_tuning(0, 0, 0) == 0
     assert _capi.launch_count() == before

@@ -171,3 +171,4 @@ def test_peer_memory_all_reduce_matches_nccl():
     # the fused sharded path bench.py runs: value vs one GPU over all shards, gradients vs single-GPU gradients, with
     # every exchange; graph replay; unequal shards caught
     assert line["sharded_loss_ok"] and line["graph_replay_ok"] and line["unequal_shards_ok"] and line["all_ok"], line
+    assert line["late_rank_ok"], "a rank arriving seconds late must be waited for, not turned into a NaN"
