@@ -12,8 +12,8 @@
 //   autograd of all of the above          -> dL/dCDF array, suffix scans,
 //                                                           normalisation chain rule, 2x
 //
-// Shared memory: first the small per-CTA structures (scan scratch, first-slot mailbox + carry per
-// chunk, mbarrier), then rows of RS floats at COMPILE-TIME offsets, so that for a CDF entry at shared
+// Shared memory: first the small per-CTA structures (scan scratch, one carry per chunk, mbarrier), then rows of
+// RS >= TPF * E + 8 floats at COMPILE-TIME offsets, so that for a CDF entry at shared
 // address a its support position is at a + POS_OFF and its dL/dCDF at a + G_OFF (immediates):
 //   rows 0, 1 : CDF of u / v, entry [n] / [m] = +inf sentinel
 //   rows 2, 3 : support positions of u / v, entry [n] / [m] repeats the last one (the reference's
@@ -28,7 +28,9 @@
 //   next 4    : (complex input, template flag CPLX) the two interleaved complex64 STFT rows: the
 //               magnitude (squared) is formed while they are read -- no |.| tensor in HBM -- and the
 //               gradient kernel overwrites them in place with the complex gradient rows
-//   then      : padding (threads whose bins lie past the end of a row read, and mask, what follows)
+//   then      : 64 bytes of padding.  Every thread loads and stores all E entries of its bins without guards: the
+//               rows are long enough, what lies past the end of the data is masked once (stage 1) or overwritten
+//               by the threads that own it (sentinels, zeroed dL/dCDF tail)
 // The raw rows of a frame arrive by TMA bulk copy (`cp.async.bulk`, SASS UBLKCP).  A 4*n-byte row
 // is only 4-byte aligned (n = 1025 / 257), the bulk unit is 16 bytes: the copy therefore fetches
 // the 16-byte aligned WINDOW around the row and the kernel skips the `lead` bytes in front.  The

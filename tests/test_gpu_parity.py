@@ -499,6 +499,29 @@ def test_hinge_gate_and_threshold(L):
         assert torch.equal(mine.reshape(30, -1).abs().sum(1) == 0, ref.reshape(30, -1).abs().sum(1) == 0), "hinge gate"
 
 
+@pytest.mark.parametrize("n_bins", [288, 289, 576, 1087, 1088, 1089, 1152])
+def test_rows_that_fill_a_kernel_configuration_exactly(L, n_bins):
+    """Row lengths at and around threads x bins-per-thread of the configurations (32x9, 64x9, 64x17, 128x9): every
+    thread's bins lie inside the row (the +inf sentinel is then written by thread 0), one bin short, one bin over
+    (next configuration).  No-cut mode: the loss is continuous there, so the reference's float32 value is the gate."""
+    gen = torch.Generator().manual_seed(n_bins)
+    x = torch.rand(6, n_bins, generator=gen) ** 4 + 1e-4
+    y = torch.rand(6, n_bins, generator=gen) ** 4 + 1e-4
+    pos = torch.linspace(0, 1, n_bins)
+    rows32, g32x, g32y = O.sot_loss_and_grads(x, y, pos, pos, stable=True, p=2, square=True)
+    _, g64x, g64y = O.sot_loss_and_grads(x.double(), y.double(), pos.double(), pos.double(), stable=True, p=2, square=True)
+    xd, yd = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
+    mod = L.Wasserstein1D(p=2, square_dist=True)
+    v = mod(xd, yd, x_pos=pos.to(DEV), y_pos=pos.to(DEV))
+    v.backward()
+    assert abs(v.item() - rows32.mean().item()) <= 1e-5 * rows32.mean().item()
+    with torch.no_grad():
+        rows = mod(xd.detach()[:, None], yd.detach()[:, None], x_pos=pos.to(DEV), y_pos=pos.to(DEV), dims=1).cpu()
+    assert torch.allclose(rows, rows32, rtol=1e-5, atol=0)
+    _assert_grad_gate(xd.grad.cpu(), g32x, g64x, f"{n_bins} bins d/dtarget", 3.0)
+    _assert_grad_gate(yd.grad.cpu(), g32y, g64y, f"{n_bins} bins d/dprediction", 3.0)
+
+
 def test_float64_inputs_are_accepted_like_the_reference(L):
     """The reference (and its `ref64` evaluation) takes float64 spectra: the drop-in converts, computes in float32
     and hands float64 values and gradients back."""
