@@ -824,17 +824,12 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         cta_sync<TPF>();
         if constexpr (WITH_GRAD && FROM_BINS) {
             // the gradient stage sums dL/dCDF over all E entries of every thread without guards: zero what lies
-            // past the end of the rows (the walk only writes real entries)
-            // (unrolled, predicated: only the warp that holds the ends of the rows takes the branch at all)
-            if (!in_u || !in_v) {
-#pragma unroll
-                for (int c = 0; c < E; ++c) {
-                    if (e0 + c >= n) sts32o<LY::G_OFF>(A0 + 4 * (e0 + c), 0.0f);
-                    if (e0 + c >= m) sts32o<LY::G_OFF>(B0 + 4 * (e0 + c), 0.0f);
-                }
-            }
+            // past the end of the rows (the walk only writes real entries).  Spread over the CTA: entry n + tid,
+            // normally one store per thread and row (nobody else touches these entries before the barriers that
+            // precede the gradient stage).
+            for (int idx = n + tid; idx < TPF * E; idx += TPF) sts32o<LY::G_OFF>(A0 + 4 * idx, 0.0f);
+            for (int idx = m + tid; idx < TPF * E; idx += TPF) sts32o<LY::G_OFF>(B0 + 4 * idx, 0.0f);
         }
-
         uint32_t adrA[NCH], adrB[NCH];
         float a[NCH], pa[NCH], b[NCH], pb[NCH], qprev[NCH];
         int i0[NCH];
