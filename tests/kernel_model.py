@@ -6,8 +6,10 @@ for a tie group inherited from earlier chunks, the scatter of dL/dCDF to the sou
 two suffix scans and the normalisation chain rule -- so the algorithm can be checked against the
 oracle on the CPU (tests/test_kernel_model.py) before and independently of any GPU run.
 Differences in arithmetic detail that the GPU tests (not this model) pin down: the kernel forms
-the CDF as fl32(prefix64 / mass) instead of cumsum64(fl32(a / mass)), obtains the mass term by
-Abel summation sum(dL/dc * c), and cuts the slots into odd-length chunks.  Test infrastructure only.
+the CDF as fl32(prefix64 / mass) instead of cumsum64(fl32(a / mass)), forms the mass term
+sum(gw * w) per thread as S_t * P_t + sum(ls * w) (P_t = the CDF-stage prefix of the thread), and cuts the
+slots into odd-length chunks.  (The peek across the chunk boundary is the thread's own state after its
+last advance -- the kernel needs no mailbox between chunks either.)  Test infrastructure only.
 """
 import numpy as np
 
