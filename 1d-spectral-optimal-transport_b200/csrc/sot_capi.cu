@@ -14,6 +14,7 @@
 
 // Production configurations (one per row-length class).  The alternatives that were only ever reachable through
 // `sot_set_tuning` are compiled in with -DSOT_TUNING_CONFIGS (`SOT_BUILD_TUNING=1 python -m sot_b200.build`).
+SOT_DECLARE_SUBWARP_CONFIG(16, 17, 280, 1)
 SOT_DECLARE_CONFIG(32, 9, 296, 1)
 SOT_DECLARE_CONFIG(64, 9, 584, 2)
 SOT_DECLARE_CONFIG(64, 17, 1096, 1)
@@ -113,12 +114,14 @@ using LaunchFn = cudaError_t (*)(const sot::LaunchRequest&, cudaStream_t);
 struct Config {
     int tpf, e, rs, nch;
     LaunchFn fn;
+    bool sub;  // sub-warp frames (several frames per warp): real spectra -> loss / gradients only
     int max_bins() const { return tpf * e < rs - 7 ? tpf * e : rs - 7; }
 };
 // Ordered by preference for a given row length: the first entry that holds the row is used
 // (choices from measurements on B200, profiles/).  Shared memory per CTA = (4 or 6) * 4 * rs bytes.
 const Config kConfigs[] = {
-    {32, 9, 296, 1, sot_launch_32_9_296_1},      // <= 288 bins   (n_fft 512: 257)
+    {16, 17, 280, 1, sot_launch_sub_16_17_280_1, true},  // <= 272 bins (n_fft 512: 257): two frames per warp
+    {32, 9, 296, 1, sot_launch_32_9_296_1},      // <= 288 bins   (one warp per frame: plans, CDF harness, raw, complex)
     {64, 9, 584, 2, sot_launch_64_9_584_2},      // <= 576 bins   (n_fft 1024: 513)
     {64, 17, 1096, 1, sot_launch_64_17_1096_1},  // <= 1088 bins  (n_fft 2048: 1025) -- measured best of the five
 #ifdef SOT_TUNING_CONFIGS
@@ -138,6 +141,7 @@ constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 thread_local char g_error[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_tune_tpf{0}, g_tune_e{0}, g_tune_nch{0};
+std::atomic<bool> g_prefer_sub{true};   // sub-warp configurations by default (when the request allows)
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -151,18 +155,20 @@ int cuda_fail(cudaError_t e, const char* what) {
     return static_cast<int>(e);
 }
 
-const Config* pick_config(int n, int m) {
+// `sub_ok`: the request is one the sub-warp configurations serve (see Config::sub)
+const Config* pick_config(int n, int m, bool sub_ok = false) {
     const int need = n > m ? n : m;
     const int tt = g_tune_tpf.load(), te = g_tune_e.load();
     if (tt != 0) {
         for (int i = 0; i < kNumConfigs; ++i) {
             const Config& c = kConfigs[i];
-            if (c.tpf == tt && c.e == te && (g_tune_nch.load() == 0 || c.nch == g_tune_nch.load()) && c.max_bins() >= need)
+            if (c.tpf == tt && c.e == te && (g_tune_nch.load() == 0 || c.nch == g_tune_nch.load()) &&
+                c.max_bins() >= need && (!c.sub || sub_ok))
                 return &c;
         }
     }
     for (int i = 0; i < kNumConfigs; ++i)
-        if (kConfigs[i].max_bins() >= need) return &kConfigs[i];
+        if (kConfigs[i].max_bins() >= need && (!kConfigs[i].sub || (sub_ok && g_prefer_sub.load()))) return &kConfigs[i];
     return nullptr;
 }
 
@@ -209,7 +215,10 @@ int launch(const sot_problem* p, sot::LaunchRequest& r, void* stream) {
     if ((p->flags & SOT_COMPLEX_INPUT) && (p->flags & SOT_RAW_WEIGHTS))
         return fail(SOT_EINVAL, "SOT_RAW_WEIGHTS rows are real weights, not complex spectra");
     if (p->n_frames == 0) return SOT_OK;
-    const Config* c = pick_config(p->n_u, p->n_v);
+    const bool sub_ok = r.mode == sot::MODE_SPECTRA && r.out != sot::OUT_PLAN &&
+                        !(p->flags & (SOT_RAW_WEIGHTS | SOT_COMPLEX_INPUT)) && r.args.coranks_in == nullptr &&
+                        r.args.coranks_out == nullptr;
+    const Config* c = pick_config(p->n_u, p->n_v, sub_ok);
     if (c == nullptr)
         return fail(SOT_ETOOBIG, "rows of %d / %d bins exceed the largest kernel configuration (%d bins)", p->n_u,
                     p->n_v, sot_max_bins(1, 1));

@@ -138,7 +138,7 @@ struct Layout {
     // small per-CTA structures first, the rows after them: a thread whose bins lie past the end of a row reads
     // (and masks) whatever follows -- after the last row that is the PAD below, never live scratch data
     static constexpr uint32_t SCRATCH = 0;                        // 8 doubles per warp
-    static constexpr uint32_t CARRY = SCRATCH + 64u * (TPF / 32);  // m*d of the group open at the end of each chunk
+    static constexpr uint32_t CARRY = SCRATCH + 64u * ((TPF + 31) / 32);  // m*d of the group open at the end of each chunk
     static constexpr uint32_t MBAR = (CARRY + 4u * NCH * TPF + 15u) & ~15u;
     static constexpr uint32_t HEAD = (MBAR + 16u + 127u) & ~127u;
     static constexpr uint32_t A = HEAD, B = HEAD + ROW;  // CDF rows (also the landing zone of the raw rows)
@@ -157,6 +157,9 @@ struct Layout {
     static constexpr uint32_t ROWS = REAL_ROWS + (CPLX ? 4 : 0);
     static constexpr uint32_t PAD = 64u;  // (rows hold TPF * E entries and the lead: nothing is read past the last row)
     static constexpr uint32_t TOTAL = HEAD + ROWS * ROW + PAD;
+    // sub-warp frames: one such block per frame of the CTA, 16 banks apart -- the 16 lanes of a frame touch 16 of the
+    // 32 banks in every blocked access (17 t mod 32), the other frame of the warp gets the other 16
+    static constexpr uint32_t SLOT = ((TOTAL + 127u) & ~127u) + 64u;
     static constexpr int MAX_BINS = RS - 7;  // sentinel + up to 3 floats of lead + rounding of the bulk window
 };
 
@@ -313,7 +316,7 @@ SOT_DEVINL double recip_f64(float x) {
 
 template <int TPF>
 SOT_DEVINL void cta_sync() {
-    if constexpr (TPF == 32) {
+    if constexpr (TPF <= 32) {  // one warp per CTA (TPF < 32: sub-warp frames, several frames in the warp)
         __syncwarp();
     } else {
         __syncthreads();
@@ -343,17 +346,21 @@ SOT_DEVINL void scan_step(double& v, int src) {
 template <int TPF, bool REVERSE, bool WANT_NEXT>
 SOT_DEVINL void cta_scan2(float ta, float tb, double& off_a, double& off_b, double& nxt_a, double& nxt_b,
                           double& total_a, double& total_b, double* slot, int tid) {
-    constexpr int NW = TPF / 32;
-    const int lane = tid & 31, w = tid >> 5;
-    const int edge = REVERSE ? 31 : 0;  // the lane with nothing before it
+    // TPF < 32 (sub-warp frames: several frames share a warp, each in its own group of TPF lanes): the scan runs
+    // inside the group -- `lane` is the position in the group, `base` the warp lane the group starts at.
+    constexpr int W = TPF < 32 ? TPF : 32;
+    constexpr int NW = (TPF + 31) / 32;
+    const int lane = tid & (W - 1), w = tid >> 5;
+    const int base = static_cast<int>(threadIdx.x & 31u) - lane;
+    const int edge = REVERSE ? W - 1 : 0;  // the lane with nothing before it
     // shift by one lane first: the inclusive scan of the shifted values is the exclusive scan
     float sa = REVERSE ? __shfl_down_sync(FULL_MASK, ta, 1) : __shfl_up_sync(FULL_MASK, ta, 1);
     float sb = REVERSE ? __shfl_down_sync(FULL_MASK, tb, 1) : __shfl_up_sync(FULL_MASK, tb, 1);
     double ea = lane == edge ? 0.0 : static_cast<double>(sa);
     double eb = lane == edge ? 0.0 : static_cast<double>(sb);
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const int src = REVERSE ? min(lane + off, 31) : max(lane - off, 0);
+    for (int off = 1; off < W; off <<= 1) {
+        const int src = base + (REVERSE ? min(lane + off, W - 1) : max(lane - off, 0));
         scan_step(ea, src);
         scan_step(eb, src);
     }
@@ -362,13 +369,13 @@ SOT_DEVINL void cta_scan2(float ta, float tb, double& off_a, double& off_b, doub
     if constexpr (NW == 1) {
         off_a = ea;
         off_b = eb;
-        total_a = __shfl_sync(FULL_MASK, wa_mine, 31 - edge);
-        total_b = __shfl_sync(FULL_MASK, wb_mine, 31 - edge);
+        total_a = __shfl_sync(FULL_MASK, wa_mine, base + W - 1 - edge);
+        total_b = __shfl_sync(FULL_MASK, wb_mine, base + W - 1 - edge);
         if constexpr (WANT_NEXT) {
             const double na = REVERSE ? __shfl_up_sync(FULL_MASK, ea, 1) : __shfl_down_sync(FULL_MASK, ea, 1);
             const double nb = REVERSE ? __shfl_up_sync(FULL_MASK, eb, 1) : __shfl_down_sync(FULL_MASK, eb, 1);
-            nxt_a = lane == 31 - edge ? total_a : na;
-            nxt_b = lane == 31 - edge ? total_b : nb;
+            nxt_a = lane == W - 1 - edge ? total_a : na;
+            nxt_b = lane == W - 1 - edge ? total_b : nb;
         }
     } else {
         if (lane == 31 - edge) {
@@ -463,11 +470,15 @@ constexpr int min_ctas(int tpf, int e, int smem_bytes, int out) {
 #ifndef SOT_REGS_LOSS_E17
 #define SOT_REGS_LOSS_E17 64
 #endif
+#ifndef SOT_REGS_GRAD_SUB
+#define SOT_REGS_GRAD_SUB 128  // one-warp CTAs with 17 bins per thread (sub-warp frames): no spills
+#endif
 #ifndef SOT_REGS_GRAD_E9
 #define SOT_REGS_GRAD_E9 128  // one warp per frame (n_fft 512): 64 -> 128 registers = no spills, +11 % (profiles/r02_tuning.txt)
 #endif
-    const int regs = out == OUT_GRAD ? (e <= 9 ? (tpf == 32 ? SOT_REGS_GRAD_E9 : 64) : (e <= 17 ? SOT_REGS_GRAD_E17 : 168))
-                                     : (e <= 9 ? 40 : (e <= 17 ? SOT_REGS_LOSS_E17 : 128));
+    const int regs = out == OUT_GRAD ? (e <= 9 ? (tpf == 32 ? SOT_REGS_GRAD_E9 : 64)
+                                              : (e <= 17 ? (tpf == 32 ? SOT_REGS_GRAD_SUB : SOT_REGS_GRAD_E17) : 168))
+                                     : (e <= 9 ? 40 : (e <= 17 ? (tpf == 32 ? 96 : SOT_REGS_LOSS_E17) : 128));
     const int by_regs = 65536 / (tpf * regs);
     const int c = by_smem < by_regs ? by_smem : by_regs;
     return c < 1 ? 1 : (c > 32 ? 32 : c);
@@ -537,10 +548,17 @@ SOT_DEVINL void finish_mean(const FrameArgs& args) {
     }
 }
 
-template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int OUT, int MODE>
-__global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH, UNI, CPLX>::TOTAL, OUT))
+// FPW > 1 ("sub-warp frames", short rows): TPF < 32 threads per frame and FPW = 32 / TPF frames per CTA, each frame in
+// its own group of TPF lanes of the one warp with its own block of shared memory, mbarrier and bulk copies.  Every
+// lane runs the same instruction stream on its own frame, so the per-frame fixed costs (scans, merge-path search,
+// reductions, bookkeeping) are paid once per warp for FPW frames.  Spectra -> loss / gradients only.
+template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int OUT, int MODE, int FPW = 1>
+__global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout<TPF, RS, OUT, NCH, UNI, CPLX>::SLOT, OUT))
     sot_frame_kernel(const FrameArgs args) {
     static_assert(NCH == 1 || NCH == 2, "one or two merge chains per thread");
+    constexpr bool SUB = FPW > 1;
+    static_assert(!SUB || (TPF * FPW == 32 && !CPLX && MODE == MODE_SPECTRA && OUT != OUT_PLAN),
+                  "sub-warp frames: one warp per CTA, real spectra, loss / gradient outputs");
     static_assert(RS >= TPF * E + 8, "rows hold every thread's E entries (stored without guards) plus the lead / sentinel");
     static_assert(!(UNI && OUT == OUT_PLAN), "the plan emitter always reads positions");
     static_assert(!CPLX || (MODE == MODE_SPECTRA && OUT != OUT_PLAN), "complex input: loss / gradient from spectra only");
@@ -549,12 +567,15 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     constexpr int CW = CPLX ? 2 : 1;  // floats per raw bin
     constexpr int NCHUNK = NCH * TPF;
     constexpr bool WITH_GRAD = (OUT == OUT_GRAD);
-    constexpr int NW = TPF / 32;
+    constexpr int NW = (TPF + 31) / 32;
+    constexpr int WG = TPF < 32 ? TPF : 32;  // lanes of a warp that work on one frame
     constexpr int SEARCH_TOP = 1 << (ilog2_ceil(TPF * E + 1) - 1);
     constexpr uint32_t NO_FIX = 0xffffffffu;
     constexpr uint32_t POS4 = LY::POS_OFF + 4;
     constexpr uint32_t LAND = LY::LAND;  // landing zone rows (u, then v at + ROW)
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem_cta[];
+    const int fslot = SUB ? static_cast<int>(threadIdx.x) / TPF : 0;  // which frame of the CTA I work on
+    unsigned char* const smem = smem_cta + fslot * LY::SLOT;
 
     const int n = args.n, m = args.m, K = n + m;
     const bool square = args.flags & FLAG_SQUARE;
@@ -571,11 +592,14 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     const uint32_t sb = smem_u32(smem);
     const uint32_t A0 = sb + LY::A, B0 = sb + LY::B;
 
-    const int tid = threadIdx.x;
+    const int tid = SUB ? static_cast<int>(threadIdx.x) % TPF : static_cast<int>(threadIdx.x);  // within my frame
     const int e0 = tid * E;
     float* const fsm = reinterpret_cast<float*>(smem);
     double* const scratch = reinterpret_cast<double*>(smem + LY::SCRATCH);
-    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem + LY::MBAR);
+    // ONE mbarrier per CTA -- also with several frames per warp: lanes that spin on different barriers leave the
+    // (hand-written) wait loop at different times and the warp stays diverged, every later shuffle takes the slow path
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_cta + LY::MBAR);
+    const bool elected = SUB ? (threadIdx.x == 0) : (tid == 0);  // issues the bulk loads of the CTA
     const uint32_t carry = sb + LY::CARRY;
     const bool in_u = e0 + E <= n, in_v = e0 + E <= m;  // all of my E bins exist (no guards needed)
 
@@ -593,7 +617,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         cnt[ch] = min(L, K - k0[ch]);  // non-increasing in the chunk index
     }
 
-    if (tid == 0) {
+    if (elected) {
         mbar_init(mbar, 1);
         fence_mbar_init();
     }
@@ -612,27 +636,58 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
     __syncthreads();
 
     const int wu = CW * n, wv = CW * m;  // floats per raw row
-    auto issue_load = [&](long long f, uint32_t lu, uint32_t lv) {  // one elected thread
-        const uint32_t bu = (lu + 4u * wu + 15u) & ~15u, bv = (lv + 4u * wv + 15u) & ~15u;
-        mbar_expect_tx(mbar, bu + bv);
-        bulk_g2s(smem + LAND, reinterpret_cast<const char*>(args.u + f * wu) - lu, bu, mbar);
-        bulk_g2s(smem + LAND + LY::LAND_ROW, reinterpret_cast<const char*>(args.v + f * wv) - lv, bv, mbar);
+    // bulk loads of the frames of one CTA iteration (base frame b): raw rows -> landing rows, one expect_tx
+    auto issue_load = [&](long long b) {  // the elected thread
+        uint32_t total = 0;
+#pragma unroll
+        for (int g = 0; g < FPW; ++g) {
+            const long long f = SUB ? min(b + g, args.n_frames - 1) : b;
+            total += ((row_lead(args.u, f, wu) + 4u * wu + 15u) & ~15u) + ((row_lead(args.v, f, wv) + 4u * wv + 15u) & ~15u);
+        }
+        mbar_expect_tx(mbar, total);
+#pragma unroll
+        for (int g = 0; g < FPW; ++g) {
+            const long long f = SUB ? min(b + g, args.n_frames - 1) : b;
+            const uint32_t lu = row_lead(args.u, f, wu), lv = row_lead(args.v, f, wv);
+            const uint32_t bu = (lu + 4u * wu + 15u) & ~15u, bv = (lv + 4u * wv + 15u) & ~15u;
+            unsigned char* const dst = smem_cta + g * LY::SLOT + LAND;
+            bulk_g2s(dst, reinterpret_cast<const char*>(args.u + f * wu) - lu, bu, mbar);
+            bulk_g2s(dst + LY::LAND_ROW, reinterpret_cast<const char*>(args.v + f * wv) - lv, bv, mbar);
+        }
+    };
+    // do ALL frames of the CTA iteration with base frame b come by bulk copy?  (warp uniform)
+    auto all_bulk = [&](long long b) {
+        bool ok = true;
+#pragma unroll
+        for (int g = 0; g < FPW; ++g) {
+            const long long f = SUB ? min(b + g, args.n_frames - 1) : b;
+            ok = ok && row_is_bulk(args.u, f, wu, args.n_frames) && row_is_bulk(args.v, f, wv, args.n_frames);
+        }
+        return ok;
     };
 
-    long long frame = blockIdx.x;
+    // Frames of this CTA: blockIdx.x * FPW + fslot, then + gridDim.x * FPW.  The loop condition is the one of frame
+    // slot 0 (warp uniform); a slot that has run out of frames redoes the LAST frame of the batch in lock step
+    // (identical values to identical addresses) and keeps it out of the sums (`active`).
+    const long long fstride = static_cast<long long>(gridDim.x) * FPW;
+    long long fbase = static_cast<long long>(blockIdx.x) * FPW;
+    auto frame_of = [&](long long b) { return SUB ? min(b + fslot, args.n_frames - 1) : b; };
+    long long frame = frame_of(fbase);
     uint32_t parity = 0;
     double cta_loss = 0.0;  // (thread 0) sum of the losses of the frames this CTA processed
     // state of the frame in flight: phases of its two rows and whether it comes by bulk copy
     uint32_t lead_in_u = 0, lead_in_v = 0;
     bool bulk_in = false;
-    if (frame < args.n_frames) {
+    if (fbase < args.n_frames) {
         lead_in_u = row_lead(args.u, frame, wu);
         lead_in_v = row_lead(args.v, frame, wv);
-        bulk_in = row_is_bulk(args.u, frame, wu, args.n_frames) && row_is_bulk(args.v, frame, wv, args.n_frames);
-        if (bulk_in && tid == 0) issue_load(frame, lead_in_u, lead_in_v);
+        bulk_in = all_bulk(fbase);
+        if (bulk_in && elected) issue_load(fbase);
     }
 
-    for (; frame < args.n_frames; frame += gridDim.x) {
+    for (; fbase < args.n_frames; fbase += fstride) {
+        frame = frame_of(fbase);
+        const bool active = !SUB || (fbase + fslot < args.n_frames);
         // ---- stage 0: the frame's raw rows are (or get) in the landing zone ----------------------
         uint32_t rawU = sb + LAND + 4u * CW * e0, rawV = sb + LAND + LY::LAND_ROW + 4u * CW * e0;  // my first raw bins
         uint32_t cur_lead_u = 0, cur_lead_v = 0;  // phase of this frame's raw rows inside the landing rows
@@ -654,11 +709,12 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         (void)cur_lead_u;
         (void)cur_lead_v;
         // the frame after this one (its load is issued further down, when the landing zone is free)
-        const long long next = frame + gridDim.x;
-        if (next < args.n_frames) {
+        const long long next = frame_of(fbase + fstride);
+        const bool has_next = fbase + fstride < args.n_frames;  // (warp uniform)
+        if (has_next) {
             lead_in_u = row_lead(args.u, next, wu);
             lead_in_v = row_lead(args.v, next, wv);
-            bulk_in = row_is_bulk(args.u, next, wu, args.n_frames) && row_is_bulk(args.v, next, wv, args.n_frames);
+            bulk_in = all_bulk(fbase + fstride);
         }
         if (!UNI && !pos_shared) {  // per-frame supports
             const float* gpu = args.pos_u + frame * args.pos_u_stride;
@@ -830,6 +886,9 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             for (int idx = n + tid; idx < TPF * E; idx += TPF) sts32o<LY::G_OFF>(A0 + 4 * idx, 0.0f);
             for (int idx = m + tid; idx < TPF * E; idx += TPF) sts32o<LY::G_OFF>(B0 + 4 * idx, 0.0f);
         }
+        int cntf[NCH];  // slots of my chunks in THIS frame (sub-warp frames: none when the frame is poisoned)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) cntf[ch] = cnt[ch];
         uint32_t adrA[NCH], adrB[NCH];
         float a[NCH], pa[NCH], b[NCH], pb[NCH], qprev[NCH];
         int i0[NCH];
@@ -909,13 +968,13 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 int s = 0;
                 if constexpr (NCH == 2) {
 #pragma unroll 2
-                    for (; s < cnt[1]; ++s) {
+                    for (; s < cntf[1]; ++s) {
                         fstep(IC<0>{});
                         fstep(IC<1>{});
                     }
                 }
 #pragma unroll 4
-                for (; s < cnt[0]; ++s) fstep(IC<0>{});
+                for (; s < cntf[0]; ++s) fstep(IC<0>{});
             }
         } else if constexpr (OUT == OUT_GRAD) {
             // ---- stage 3b (gradient): walk + dL/dCDF -----------------------------------------------------
@@ -923,7 +982,15 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
             // slot: G = (m*d)_group - (m*d)_next group.  It is stored one step later,
             // when the next slot is known.  (It cannot overwrite the consumed CDF entry or its position:
             // a slower thread may still load that entry as the head that ends its own range.)
-            if (finite) {
+            if constexpr (SUB) {
+                // the frames of a warp may differ in `finite`, and the block below contains warp barriers: a
+                // poisoned frame goes through it with empty chunks (no slot is walked, nothing is stored)
+                if (!finite) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) cntf[ch] = 0;
+                }
+            }
+            if (SUB || finite) {
                 float md_prev[NCH];
                 bool inherited[NCH];  // the open group started before my chunk: its m*d is not known yet
                 uint32_t consumed[NCH], fix[NCH];
@@ -936,7 +1003,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     md_prev[ch] = inherited[ch] ? 0.0f : fm;
                     float dq = q - qprev[ch];
                     dq = (q > thr) ? 0.0f : dq;
-                    if (cnt[ch] > 0) {
+                    if (cntf[ch] > 0) {
                         acc[ch] = fmaf(dq, D, acc[ch]);
                         qprev[ch] = q;
                     }
@@ -945,7 +1012,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 }
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch)
-                    if (cnt[ch] > 0) {
+                    if (cntf[ch] > 0) {
                         if constexpr (UNI)
                             advance_uni(a[ch], pa[ch], b[ch], adrA[ch], adrB[ch], consumed[ch], hstep, -hstep, wk);
                         else
@@ -974,17 +1041,17 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 int s = 1;
                 if constexpr (NCH == 2) {
 #pragma unroll 2
-                    for (; s < cnt[1]; ++s) {
+                    for (; s < cntf[1]; ++s) {
                         gstep(IC<0>{});
                         gstep(IC<1>{});
                     }
                 }
 #pragma unroll 4
-                for (; s < cnt[0]; ++s) gstep(IC<0>{});
+                for (; s < cntf[0]; ++s) gstep(IC<0>{});
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                     float carry_out = -1.0f;  // -1 = "my whole chunk continues a group opened before it"
-                    if (cnt[ch] > 0) {
+                    if (cntf[ch] > 0) {
                         // The slot after my chunk = the first slot of the next chunk (or the virtual slot K: both
                         // heads are the +inf sentinels, a new group with m*d = 0): my heads after the last advance
                         // ARE that slot -- the same shared-memory entries and the same position difference the
@@ -1029,7 +1096,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     int i = i0[ch], j = k0[ch] - i0[ch], is = 0, js = 0;
                     bool inherited = (k0[ch] != 0);
                     n_inherited[ch] = 0;
-                    for (int s = 0; s < cnt[ch]; ++s) {
+                    for (int s = 0; s < cntf[ch]; ++s) {
                         const float q = fminf(a[ch], b[ch]);
                         const bool take_v = b[ch] < a[ch];
                         if (q != qprev[ch]) {
@@ -1053,7 +1120,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                         advance<POS4>(a[ch], pa[ch], b[ch], pb[ch], adrA[ch], adrB[ch], consumed, wk);
                     }
                     sts32(carry + 4u * (NCH * tid + ch),
-                          __int_as_float((cnt[ch] == 0 || inherited) ? -1 : ((is << 16) | js)));
+                          __int_as_float((cntf[ch] == 0 || inherited) ? -1 : ((is << 16) | js)));
                 }
                 cta_sync<TPF>();
 #pragma unroll
@@ -1090,13 +1157,13 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
         auto reduce_loss_in_warp = [&]() {
             part = static_cast<double>(NCH == 2 ? acc[0] + acc[NCH - 1] : acc[0]);
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULL_MASK, part, off);
+            for (int off = WG / 2; off > 0; off >>= 1) part += __shfl_xor_sync(FULL_MASK, part, off);
         };
         auto write_loss = [&]() {
             if (tid == 0) {
                 const float frame_loss = finite ? static_cast<float>(part) : f_nan();
                 if (args.loss != nullptr) args.loss[frame] = frame_loss;
-                cta_loss += static_cast<double>(frame_loss);
+                if (active) cta_loss += static_cast<double>(frame_loss);
             }
         };
         if constexpr (!MERGED) {
@@ -1115,7 +1182,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
 
         if constexpr (!WITH_GRAD) {
             // the landing zone (CDF rows) is free: fetch the next frame
-            if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
+            if (elected && has_next && bulk_in) issue_load(fbase + fstride);
         } else {
             // ---- stages 4 + 5: gradient rows, written over the dL/dCDF rows at the phase (address mod 16)
             // of their destination so that the aligned middle can leave by bulk store --------------------
@@ -1168,7 +1235,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 double dot_u = static_cast<double>(su) * base_mass_u + static_cast<double>(du);
                 double dot_v = static_cast<double>(sv) * base_mass_v + static_cast<double>(dv);
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
+                for (int off = WG / 2; off > 0; off >>= 1) {
                     dot_u += __shfl_xor_sync(FULL_MASK, dot_u, off);
                     dot_v += __shfl_xor_sync(FULL_MASK, dot_v, off);
                 }
@@ -1202,7 +1269,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                 // every thread has read its dL/dCDF entries and is done with the CDF rows (barrier above): the CDF
                 // rows can take the next frame, the dL/dCDF rows the finished gradients
                 if constexpr (!CPLX) {  // (complex: the landing rows are the output staging, see below)
-                    if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
+                    if (elected && has_next && bulk_in) issue_load(fbase + fstride);
                 }
                 // a clamped mass has no derivative (torch.where picks the constant branch)
                 const double corr_u = u_live ? (cut_scale ? dot_u + dot_v : dot_u) : 0.0;
@@ -1267,7 +1334,7 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     og_v[c] = (e0 + c < m) ? lds32(GB0 + 4 * (e0 + c)) : 0.0f;
                 }
                 cta_sync<TPF>();
-                if (tid == 0 && next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
+                if (elected && has_next && bulk_in) issue_load(fbase + fstride);
 #pragma unroll
                 for (int c = 0; c < E; ++c) {
                     if (e0 + c < n) sts32(GA0 + lead_u + 4 * (e0 + c), og_u[c]);
@@ -1305,13 +1372,20 @@ __global__ void __launch_bounds__(TPF, min_ctas(TPF, E, Layout<TPF, RS, OUT, NCH
                     cta_sync<TPF>();
                     if (tid == 0) {
                         bulk_wait_read_all();
-                        if (next < args.n_frames && bulk_in) issue_load(next, lead_in_u, lead_in_v);
+                        if (has_next && bulk_in) issue_load(fbase + fstride);
                     }
                 }
             }
         }
     }
-    if (tid == 0 && args.loss_sum != nullptr) {
+    if constexpr (SUB) {  // the frames of the warp kept their own sums (lane 0 of each group): fold them into lane 0
+#pragma unroll
+        for (int g = 1; g < FPW; ++g) {
+            const double other = __shfl_sync(FULL_MASK, cta_loss, g * TPF);
+            if (threadIdx.x == 0) cta_loss += other;
+        }
+    }
+    if (threadIdx.x == 0 && args.loss_sum != nullptr) {
         atomicAdd(args.loss_sum, cta_loss);  // one atomic per CTA
         if (args.ticket != nullptr) finish_mean(args);
     }

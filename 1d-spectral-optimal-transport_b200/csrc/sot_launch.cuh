@@ -15,10 +15,11 @@ struct LaunchRequest {
     int mode;  // MODE_SPECTRA / MODE_CDF
 };
 
-template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int OUT, int MODE>
+template <int TPF, int E, int RS, int NCH, bool UNI, bool CPLX, int PMODE, int OUT, int MODE, int FPW = 1>
 cudaError_t launch_one(const FrameArgs& a, cudaStream_t stream) {
-    auto kernel = sot_frame_kernel<TPF, E, RS, NCH, UNI, CPLX, PMODE, OUT, MODE>;
-    constexpr int smem_bytes = static_cast<int>(Layout<TPF, RS, OUT, NCH, UNI, CPLX>::TOTAL);
+    auto kernel = sot_frame_kernel<TPF, E, RS, NCH, UNI, CPLX, PMODE, OUT, MODE, FPW>;
+    constexpr int smem_bytes = static_cast<int>(FPW == 1 ? Layout<TPF, RS, OUT, NCH, UNI, CPLX>::TOTAL
+                                                         : FPW * Layout<TPF, RS, OUT, NCH, UNI, CPLX>::SLOT);
     // per instantiation AND device: opt-in shared memory size and the persistent grid size.  The forward is launched
     // from the caller's thread, the backward from the autograd engine's thread of that device, and one process may
     // drive several devices: one atomic slot per device ordinal, 0 = not set up yet.  Two threads that both see 0
@@ -33,16 +34,37 @@ cudaError_t launch_one(const FrameArgs& a, cudaStream_t stream) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return e;
         int per_sm = 0, sms = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPF, smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPF * FPW, smem_bytes);
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         cached_grid = (per_sm < 1 ? 1 : per_sm) * sms;  // persistent: every CTA slot of the chip, once
         if (dev >= 0 && dev < kMaxDev) grid_of_dev[dev].store(cached_grid, std::memory_order_release);
     }
-    const unsigned grid = static_cast<unsigned>(a.n_frames < cached_grid ? a.n_frames : cached_grid);
-    kernel<<<grid, TPF, smem_bytes, stream>>>(a);
+    const long long ctas = (a.n_frames + FPW - 1) / FPW;  // FPW frames per CTA and iteration
+    const unsigned grid = static_cast<unsigned>(ctas < cached_grid ? ctas : cached_grid);
+    kernel<<<grid, TPF * FPW, smem_bytes, stream>>>(a);
     return cudaGetLastError();
+}
+
+// Sub-warp frames (FPW frames per warp, TPF = 32 / FPW threads each): real spectra -> loss / gradients only; the
+// caller keeps the one-warp-per-frame configuration for everything else (plans, injected CDFs, raw weights, complex).
+template <int TPF, int E, int RS, int NCH, int FPW>
+cudaError_t launch_subwarp(const LaunchRequest& r, cudaStream_t stream) {
+    const FrameArgs& a = r.args;
+    const bool uniform = (a.flags & FLAG_UNIFORM) && a.pos_u_stride == 0 && a.pos_v_stride == 0 && a.n >= 2;
+    const bool p2 = (a.p == 2.0f);
+    const bool grad = (r.out == OUT_GRAD);
+    if (uniform) {
+        if (grad) return p2 ? launch_one<TPF, E, RS, NCH, true, false, 2, OUT_GRAD, MODE_SPECTRA, FPW>(a, stream)
+                            : launch_one<TPF, E, RS, NCH, true, false, 0, OUT_GRAD, MODE_SPECTRA, FPW>(a, stream);
+        return p2 ? launch_one<TPF, E, RS, NCH, true, false, 2, OUT_LOSS, MODE_SPECTRA, FPW>(a, stream)
+                  : launch_one<TPF, E, RS, NCH, true, false, 0, OUT_LOSS, MODE_SPECTRA, FPW>(a, stream);
+    }
+    if (grad) return p2 ? launch_one<TPF, E, RS, NCH, false, false, 2, OUT_GRAD, MODE_SPECTRA, FPW>(a, stream)
+                        : launch_one<TPF, E, RS, NCH, false, false, 0, OUT_GRAD, MODE_SPECTRA, FPW>(a, stream);
+    return p2 ? launch_one<TPF, E, RS, NCH, false, false, 2, OUT_LOSS, MODE_SPECTRA, FPW>(a, stream)
+              : launch_one<TPF, E, RS, NCH, false, false, 0, OUT_LOSS, MODE_SPECTRA, FPW>(a, stream);
 }
 
 template <int TPF, int E, int RS, int NCH, bool UNI>
@@ -94,3 +116,9 @@ cudaError_t launch_config(const LaunchRequest& r, cudaStream_t stream) {
     }
 #define SOT_DECLARE_CONFIG(TPF, E, RS, NCH) \
     cudaError_t sot_launch_##TPF##_##E##_##RS##_##NCH(const sot::LaunchRequest& r, cudaStream_t stream);
+#define SOT_DEFINE_SUBWARP_CONFIG(TPF, E, RS, NCH, FPW)                                                        \
+    cudaError_t sot_launch_sub_##TPF##_##E##_##RS##_##NCH(const sot::LaunchRequest& r, cudaStream_t stream) { \
+        return sot::launch_subwarp<TPF, E, RS, NCH, FPW>(r, stream);                                           \
+    }
+#define SOT_DECLARE_SUBWARP_CONFIG(TPF, E, RS, NCH) \
+    cudaError_t sot_launch_sub_##TPF##_##E##_##RS##_##NCH(const sot::LaunchRequest& r, cudaStream_t stream);

@@ -214,19 +214,33 @@ def test_kernel_cdfs_within_ulps_of_fp64(capi, L, name):
 
 @pytest.mark.parametrize("name", G.MODULE_CASES)
 @pytest.mark.parametrize("mode", ["onepass", "recompute"])
-def test_module_forward_backward_vs_reference_fixture(capi, L, name, mode):
+@pytest.mark.parametrize("short_rows", ["two frames per warp", "one warp per frame"])
+def test_module_forward_backward_vs_reference_fixture(capi, L, name, mode, short_rows):
+    """`short_rows`: rows of <= 272 bins run two frames per warp by default (16 threads x 17 bins per frame); the
+    quantile taps that give the kernel's own CDFs for gate (a) come from the one-warp-per-frame kernels (32 x 9:
+    other local sums, CDFs a few ulp apart), so gate (a) is checked with that configuration selected and the
+    default one goes through everything else."""
     g = G.load(name)
     ctor = dict(g["meta"]["ctor"])
     kw = G.oracle_kwargs(ctor)
+    F = g["x"].shape[-1]
+    default_is_sub = F <= 272
+    if short_rows == "one warp per frame" and not default_is_sub:
+        pytest.skip("only rows of <= 272 bins have the two configurations")
+    same_cdfs = not (default_is_sub and short_rows == "two frames per warp")
     mod = L.Wasserstein1D(**ctor, backward_mode=mode)
     x = g["x"].to(DEV).requires_grad_(True)
     y = g["y"].to(DEV).requires_grad_(True)
     px, py = g["pos_x"].to(DEV), g["pos_y"].to(DEV)
-    value = mod(x, y, x_pos=px, y_pos=py)
-    value.backward()
-    F = g["x"].shape[-1]
-    with torch.no_grad():
-        rows = mod(g["x"].reshape(-1, 1, F).to(DEV), g["y"].reshape(-1, 1, F).to(DEV), x_pos=px, y_pos=py, dims=1)
+    if short_rows == "one warp per frame":
+        _tune(capi, (32, 9, 1))
+    try:
+        value = mod(x, y, x_pos=px, y_pos=py)
+        value.backward()
+        with torch.no_grad():
+            rows = mod(g["x"].reshape(-1, 1, F).to(DEV), g["y"].reshape(-1, 1, F).to(DEV), x_pos=px, y_pos=py, dims=1)
+    finally:
+        capi.set_tuning(0, 0, 0)
     assert value.shape == g["value"].shape and rows.shape == g["rows"].shape
     assert x.grad.shape == g["grad_x"].shape and y.grad.shape == g["grad_y"].shape
     ref_rows = g["rows"]
@@ -254,6 +268,8 @@ def test_module_forward_backward_vs_reference_fixture(capi, L, name, mode):
     ref_gy = g["grad_y"].reshape(-1, F)[:, perm].numpy() * rows.numel()
     f8 = np.float64
     for r in range(xs.shape[0]):
+        if not same_cdfs:
+            break  # (gate (a) needs the CDFs of the configuration that ran: see the docstring)
         tl, tgx, tgy = O.fp64_chain_from_cdfs(xs[r].numpy(), ys[r].numpy(), cu[r], cv[r], pos.numpy(), pos.numpy(),
                                               mass_u[r], mass_v[r], kw["p"], kw["square"], kw["cut_scale"],
                                               kw["limit"])
@@ -432,13 +448,16 @@ PAPER_CONFIGS = {"SOT-2048": (2048, True, "linear"), "SOT-512": (512, True, "lin
 
 @pytest.mark.parametrize("config", sorted(PAPER_CONFIGS))
 @pytest.mark.parametrize("mode", ["onepass", "recompute"])
-def test_parity_at_the_papers_batch_size(L, config, mode):
+@pytest.mark.parametrize("tuning", [(0, 0), (16, 17, 1), (32, 9, 1)])
+def test_parity_at_the_papers_batch_size(capi, L, config, mode, tuning):
     """The module as the trainer calls it (trainer.py:209-221) on 1024 synthetic frames, against the reference's
     float32 evaluation (the pinned oracle) and its float64 evaluation.  Bounds = the north star's 1e-5 on the batch
     loss in EVERY mode (measured 1e-7 .. 3.3e-6, profiles/r01j_parity_at_scale.jsonl) and the fp64-relative
     gradient gate."""
     from sot_b200 import synthetic as S
     n_fft, cut, grid = PAPER_CONFIGS[config]
+    if tuning[0] and n_fft != 512:
+        pytest.skip("the short-row configurations (two frames per warp / one warp per frame) hold 257 bins")
     x, y = S.sot_batch(64, n_fft, seed=42)
     pos = S.linear_positions(n_fft) if grid == "linear" else S.logf_positions(n_fft)
     kw = dict(p=2, square=True, cut_scale=cut, limit=cut)
@@ -446,13 +465,17 @@ def test_parity_at_the_papers_batch_size(L, config, mode):
     rows64, g64x, g64y = O.sot_loss_and_grads(x.double(), y.double(), pos.double(), pos.double(), stable=True, **kw)
     mod = L.Wasserstein1D(p=2, square_dist=True, dont_normalize=cut, limit_quantile_range=cut, backward_mode=mode)
     xd, yd = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
-    value = mod(xd, yd, x_pos=pos.to(DEV), y_pos=pos.to(DEV))
-    value.backward()
+    _tune(capi, tuning)
+    try:
+        value = mod(xd, yd, x_pos=pos.to(DEV), y_pos=pos.to(DEV))
+        value.backward()
+        with torch.no_grad():
+            rows = mod(x.reshape(-1, 1, x.shape[-1]).to(DEV), y.reshape(-1, 1, y.shape[-1]).to(DEV),
+                       x_pos=pos.to(DEV), y_pos=pos.to(DEV), dims=1).cpu()
+    finally:
+        capi.set_tuning(0, 0, 0)
     ref_mean = rows32.double().mean().item()
     assert abs(value.item() - ref_mean) <= 1e-5 * abs(ref_mean), (config, value.item(), ref_mean)
-    with torch.no_grad():
-        rows = mod(x.reshape(-1, 1, x.shape[-1]).to(DEV), y.reshape(-1, 1, y.shape[-1]).to(DEV), x_pos=pos.to(DEV),
-                   y_pos=pos.to(DEV), dims=1).cpu()
     # per frame: no further from the float64 value than the reference's float32 value is, on average
     e_mine = (rows.reshape(-1).double() - rows64).abs().mean().item()
     e_ref = (rows32.double() - rows64).abs().mean().item()
@@ -520,6 +543,51 @@ def test_rows_that_fill_a_kernel_configuration_exactly(L, n_bins):
     assert torch.allclose(rows, rows32, rtol=1e-5, atol=0)
     _assert_grad_gate(xd.grad.cpu(), g32x, g64x, f"{n_bins} bins d/dtarget", 3.0)
     _assert_grad_gate(yd.grad.cpu(), g32y, g64y, f"{n_bins} bins d/dprediction", 3.0)
+
+
+@pytest.mark.parametrize("n_frames", [1, 2, 3, 7, 33])
+@pytest.mark.parametrize("p,cut,grid", [(2, True, "linear"), (2, False, "logf"), (1, False, "linear"), (3, True, "linear")])
+def test_two_frames_per_warp_configuration(capi, L, n_frames, p, cut, grid):
+    """The sub-warp configuration for short rows (16 threads per frame, two frames per warp) against the
+    one-warp-per-frame kernels and the oracle: odd frame counts (the spare half-warp redoes the last frame), a
+    poisoned frame next to a healthy one in the same warp, both grids, three p."""
+    from sot_b200 import synthetic as S
+    x, y = S.sot_batch(3, 512, seed=7 + n_frames)
+    x, y = x.reshape(-1, 257)[:n_frames].clone(), y.reshape(-1, 257)[:n_frames].clone()
+    if n_frames >= 3:
+        x[1, 5] = float("nan")  # poisons frame 1 only
+    pos = S.linear_positions(512) if grid == "linear" else S.logf_positions(512)
+    ctor = dict(p=p, square_dist=True, dont_normalize=cut, limit_quantile_range=cut)
+    out = {}
+    for name, tuning in (("warp", (32, 9, 1)), ("half", (16, 17, 1))):
+        _tune(capi, tuning)
+        try:
+            xd, yd = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
+            rows = L.Wasserstein1D(**ctor)(xd[:, None], yd[:, None], x_pos=pos.to(DEV), y_pos=pos.to(DEV), dims=1)
+            rows.nansum().backward()
+            mean = L.Wasserstein1D(**ctor)(x.to(DEV), y.to(DEV), x_pos=pos.to(DEV), y_pos=pos.to(DEV))
+            with torch.no_grad():
+                fwd = L.Wasserstein1D(**ctor)(x.to(DEV)[:, None], y.to(DEV)[:, None], x_pos=pos.to(DEV),
+                                              y_pos=pos.to(DEV), dims=1)
+        finally:
+            capi.set_tuning(0, 0, 0)
+        out[name] = (rows.detach().cpu(), xd.grad.cpu(), yd.grad.cpu(), mean.item(), fwd.cpu())
+    a, b = out["warp"], out["half"]
+    ok = torch.isfinite(a[0])
+    assert torch.equal(ok, torch.isfinite(b[0])) and (n_frames < 3 or not ok[1]) and ok.sum() >= n_frames - 1
+    assert torch.equal(b[0][ok], b[4][ok]), "forward-only and fused kernels of the sub-warp configuration disagree"
+    # the two configurations sum different groups of bins locally: CDFs a few ulp apart
+    assert torch.allclose(a[0][ok], b[0][ok], rtol=(2e-4 if cut else 2e-6), atol=1e-9)
+    assert (a[3] != a[3]) == (b[3] != b[3]) and (a[3] != a[3] or abs(a[3] - b[3]) <= (2e-4 if cut else 2e-6) * abs(a[3]))
+    for ga, gb in ((a[1], b[1]), (a[2], b[2])):
+        assert torch.equal(torch.isnan(ga).any(1), ~ok) and torch.equal(torch.isnan(gb).any(1), ~ok)
+        assert _rel_l2(gb[ok], ga[ok]) <= 5e-3
+    # and against the reference's formula in float64 (healthy frames)
+    kw = dict(p=p, square=True, cut_scale=cut, limit=cut)
+    r64 = O.sot_per_frame(x[ok].double(), y[ok].double(), pos.double(), pos.double(), **kw)
+    r32 = O.sot_per_frame(x[ok], y[ok], pos, pos, **kw)
+    tol = torch.maximum(torch.full_like(r64, 1e-5), 1.5 * (r32.double() - r64).abs() / r64.abs())
+    assert ((b[0][ok].double() - r64).abs() <= tol * r64.abs() + 1e-12).all()
 
 
 def test_float64_inputs_are_accepted_like_the_reference(L):
