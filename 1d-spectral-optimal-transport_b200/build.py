@@ -29,7 +29,7 @@ def _nvcc() -> str:
 
 
 # configurations that only `sot_set_tuning` could ever reach: compiled with SOT_BUILD_TUNING=1
-TUNING_ONLY = ("sot_cfg_32_9_296_2", "sot_cfg_64_17_1096_2", "sot_cfg_32_33_1064_2", "sot_cfg_32_33_1064_1")
+TUNING_ONLY = ("sot_cfg_32_9_296_2", "sot_cfg_64_17_1096_2", "sot_cfg_32_33_1064_2")
 
 
 def _tuning() -> bool:

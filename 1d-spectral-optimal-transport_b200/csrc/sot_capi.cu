@@ -17,6 +17,7 @@
 SOT_DECLARE_SUBWARP_CONFIG(16, 17, 280, 1)
 SOT_DECLARE_CONFIG(32, 9, 296, 1)
 SOT_DECLARE_CONFIG(64, 9, 584, 2)
+SOT_DECLARE_CONFIG(32, 33, 1064, 1)
 SOT_DECLARE_CONFIG(64, 17, 1096, 1)
 SOT_DECLARE_CONFIG(128, 9, 1160, 1)
 SOT_DECLARE_CONFIG(128, 17, 2184, 2)
@@ -26,7 +27,6 @@ SOT_DECLARE_CONFIG(256, 33, 8456, 1)
 SOT_DECLARE_CONFIG(32, 9, 296, 2)
 SOT_DECLARE_CONFIG(64, 17, 1096, 2)
 SOT_DECLARE_CONFIG(32, 33, 1064, 2)
-SOT_DECLARE_CONFIG(32, 33, 1064, 1)
 #endif
 
 namespace sot {
@@ -123,13 +123,14 @@ const Config kConfigs[] = {
     {16, 17, 280, 1, sot_launch_sub_16_17_280_1, true},  // <= 272 bins (n_fft 512: 257): two frames per warp
     {32, 9, 296, 1, sot_launch_32_9_296_1},      // <= 288 bins   (one warp per frame: plans, CDF harness, raw, complex)
     {64, 9, 584, 2, sot_launch_64_9_584_2},      // <= 576 bins   (n_fft 1024: 513)
-    {64, 17, 1096, 1, sot_launch_64_17_1096_1},  // <= 1088 bins  (n_fft 2048: 1025) -- measured best of the five
+    {32, 33, 1064, 1, sot_launch_32_33_1064_1},  // <= 1056 bins  (n_fft 2048: 1025): ONE WARP per frame, 33 bins per thread --
+                                                 // no CTA barriers, half the per-frame fixed cost; since the gradient stage
+                                                 // rebuilds its suffix sums (162 registers, no spills) 14 % faster than 64 x 17
+    {64, 17, 1096, 1, sot_launch_64_17_1096_1},  // <= 1088 bins  (two warps per frame: the round-1 / early round-2 choice)
 #ifdef SOT_TUNING_CONFIGS
     {32, 9, 296, 2, sot_launch_32_9_296_2},      // two-chain variant: measured slower
     {64, 17, 1096, 2, sot_launch_64_17_1096_2},  // alternatives for 1025 bins (profiles/r01j_tuning_experiments.txt)
-    {32, 33, 1064, 2, sot_launch_32_33_1064_2},
-    {32, 33, 1064, 1, sot_launch_32_33_1064_1},  // one warp per frame, one chain: the loss-only kernel is 8 % faster
-                                                 // than 64 x 17, the gradient kernel 20 % slower -- 168 registers
+    {32, 33, 1064, 2, sot_launch_32_33_1064_2},  // two merge chains per thread: 165 vs 182 M frames/s
 #endif
     {128, 9, 1160, 1, sot_launch_128_9_1160_1},    // <= 1152 bins
     {128, 17, 2184, 2, sot_launch_128_17_2184_2},  // <= 2176 bins  (n_fft 4096: 2049)

@@ -769,6 +769,8 @@ __global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout
             // spectra (every `Wasserstein1D` call) take the packed fp32 route: a few ulp, at a third of the
             // instructions.
             constexpr bool exact = (MODE == MODE_RAW);
+            constexpr int NSEG = E >= 25 ? 4 : 1;  // segments of a thread's local prefix sums (see pass 1)
+            auto seg_begin = [](int s) constexpr { return (E * s) / NSEG; };
             double off_u, off_v, nxt_u = 0.0, nxt_v = 0.0, tot_u, tot_v;
             if constexpr (exact) {
                 off_u = off_v = 0.0;
@@ -781,13 +783,22 @@ __global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout
                 }
                 cta_scan2d<TPF>(off_u, off_v, tot_u, tot_v, scratch, tid);
             } else {
+                // Long local runs (33 bins per thread) are summed in NSEG independent segments: the fp32 rounding
+                // error of a local prefix grows with the number of adds behind it (33 sequential adds: up to 5 ulp
+                // of the fp64 CDF on the paper's spectra, four runs of 8 or 9: <= 3), and four short dependency
+                // chains issue faster than one long one.
                 f32x2 t2 = 0;
-                if (sq) {  // (uniform branch: a per-element select costs three extra instructions)
 #pragma unroll
-                    for (int c = 0; c < E; ++c) t2 = fma2(x2[c], x2[c], t2);  // (the same instruction as in pass 2:
-                } else {                                                      //  T is its last prefix)
+                for (int s = 0; s < NSEG; ++s) {
+                    f32x2 acc2 = 0;
+                    if (sq) {  // (uniform branch: a per-element select costs three extra instructions)
 #pragma unroll
-                    for (int c = 0; c < E; ++c) t2 = add2(t2, x2[c]);
+                        for (int c = seg_begin(s); c < seg_begin(s + 1); ++c) acc2 = fma2(x2[c], x2[c], acc2);
+                    } else {   // (the same instructions as in pass 2: a segment's sum is its last prefix)
+#pragma unroll
+                        for (int c = seg_begin(s); c < seg_begin(s + 1); ++c) acc2 = add2(acc2, x2[c]);
+                    }
+                    t2 = NSEG == 1 ? acc2 : add2(t2, acc2);
                 }
                 float Tu, Tv;
                 unpack2(t2, Tu, Tv);
@@ -835,15 +846,26 @@ __global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout
                 // code path -- the few threads whose bins straddle or lie past the end of a row used to drag
                 // their whole warp through a second, guarded copy of this loop.  What they wrote past the row is
                 // overwritten below (sentinels).
+                // Segments (NSEG > 1): a segment's prefixes restart from 0 and ride on `sbl2` = the pre-head value of
+                // the previous segment's LAST entry (tail + everything before the segment, already scaled), so an
+                // entry still costs one FFMA2 + one FADD2, nothing is carried from pass 1, and -- fma and add being
+                // monotone in the prefix -- a segment's entries start from the last entry of the one before: the
+                // row is non-decreasing across segment boundaries by construction.
                 auto emit = [&](auto SQ) {
-                    f32x2 p2 = 0;
+                    f32x2 sbl2 = bl2;
 #pragma unroll
-                    for (int c = 0; c < E; ++c) {
-                        p2 = decltype(SQ)::value ? fma2(x2[c], x2[c], p2) : add2(p2, x2[c]);
-                        float ca, cb;
-                        unpack2(add2(fma2(p2, inv2, bl2), bh2), ca, cb);
-                        sts32(A0 + 4 * (e0 + c), fminf(ca, cap_u));
-                        sts32(B0 + 4 * (e0 + c), fminf(cb, cap_v));
+                    for (int s = 0; s < NSEG; ++s) {
+                        f32x2 p2 = 0, in2 = sbl2;
+#pragma unroll
+                        for (int c = seg_begin(s); c < seg_begin(s + 1); ++c) {
+                            p2 = decltype(SQ)::value ? fma2(x2[c], x2[c], p2) : add2(p2, x2[c]);
+                            in2 = fma2(p2, inv2, sbl2);
+                            float ca, cb;
+                            unpack2(add2(in2, bh2), ca, cb);
+                            sts32(A0 + 4 * (e0 + c), fminf(ca, cap_u));
+                            sts32(B0 + 4 * (e0 + c), fminf(cb, cap_v));
+                        }
+                        sbl2 = in2;
                     }
                 };
                 if (sq) emit(std::true_type{}); else emit(std::false_type{});  // (uniform branch)

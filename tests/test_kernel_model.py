@@ -103,7 +103,7 @@ def test_end_to_end_model_vs_stable_autograd(cut):
 def test_cdf_stage_model_is_monotone_and_tracks_fp64(threads, per_thread, n):
     """The design argument of the packed-fp32 CDF stage, checked on the CPU model for adversarial rows: the row is
     non-decreasing across thread boundaries (the cap by the next thread's head), ends at fl32(total / mass), and
-    stays within ~E/2 ulp of the float64 CDF."""
+    stays within ~(longest local run)/2 ulp of the float64 CDF."""
     rng = np.random.default_rng(threads * 1000 + n)
     rows = [np.exp(6.0 * rng.standard_normal(n) - 8.0), rng.random(n), np.full(n, 0.37),
             np.where(rng.random(n) < 0.02, 1.0, 1e-7 * rng.random(n)),   # isolated peaks over a noise floor
@@ -116,7 +116,8 @@ def test_cdf_stage_model_is_monotone_and_tracks_fp64(threads, per_thread, n):
         mass = max(float(np.float32(w.sum())), 1e-7)  # utils.py:135-142: a mass <= eps is replaced by eps
         c64 = np.cumsum(w) / mass
         ulp = np.spacing(c64.astype(np.float32))
-        assert np.max(np.abs(c.astype(np.float64) - c64) / ulp) <= per_thread / 2 + 2
+        longest = max(np.diff(KM.cdf_segments(per_thread)))  # fp32 adds behind a local prefix
+        assert np.max(np.abs(c.astype(np.float64) - c64) / ulp) <= longest / 2 + 2 + len(KM.cdf_segments(per_thread)) / 2
         assert abs(float(c[-1]) - c64[-1]) <= 1.2e-7 * c64[-1]
 
 
@@ -144,3 +145,27 @@ def test_cutoff_mask_on_the_fma_pipe_is_exactly_zero_or_one():
     assert all(keep(q, keep_c) == 0.0 for q in above if q > 1.0)
     finite = [f32(0.0), f32(1.0), f32(7.0), f32(3.4e38)]
     assert all(keep(q, np.float64(np.inf)) == 1.0 for q in finite) and keep(f32(np.inf), np.float64(np.inf)) == 0.0
+
+
+@pytest.mark.parametrize("name", ["sot2048_cut", "sot2048_nocut", "sot2048_logf_unsorted"])
+def test_cdf_stage_model_on_the_reference_fixtures_one_warp_per_frame(name):
+    """The production configuration for 1025 bins is one warp per frame, 33 bins per thread.  33 sequential fp32
+    adds leave the CDF up to 5 ulp from the float64 CDF on these fixtures; with the local prefix sums restarted in
+    four segments the model -- which the GPU test `test_kernel_cdfs_within_ulps_of_fp64` shows the kernel
+    follows -- stays within 3 (the reference's own float32 CDFs: within 3)."""
+    from tests import golden_io as G
+    g = G.load(name)
+    kw = G.oracle_kwargs(g["meta"]["ctor"])
+    F = g["x"].shape[-1]
+    x, y = g["x"].reshape(-1, F), g["y"].reshape(-1, F)
+    wx, wy = O.spectra_to_weights(x.double(), y.double(), kw["square"], kw["cut_scale"])
+    c64u, c64v = torch.cumsum(wx, 1).float().numpy(), torch.cumsum(wy, 1).float().numpy()
+
+    def ulps(a, b):
+        return int(np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64)).max())
+
+    for r in range(x.shape[0]):
+        cu, inv = KM.cdf_stage_model(x[r].numpy(), 32, 33, square=kw["square"], return_inv=True)
+        cv = KM.cdf_stage_model(y[r].numpy(), 32, 33, square=kw["square"], inv64=inv if kw["cut_scale"] else None)
+        assert np.all(np.diff(cu) >= 0) and np.all(np.diff(cv) >= 0)
+        assert ulps(cu, c64u[r]) <= 3 and ulps(cv, c64v[r]) <= 3, (r, ulps(cu, c64u[r]), ulps(cv, c64v[r]))
