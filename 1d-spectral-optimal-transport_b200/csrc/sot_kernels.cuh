@@ -745,8 +745,18 @@ __global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout
             // Pass 1: my E (u, v) bin pairs -> values to accumulate (x, x^2, |z| or |z|^2) and their local
             // sums, in packed fp32.  The per-thread sums T are then scanned across the CTA in fp64.
             const bool inside = in_u && in_v;
+            // One-warp CTAs: the entries between the end of a raw row and the end of the last thread's bins are
+            // zeroed IN the landing row (one store per thread and row, a warp barrier), so nobody masks what it
+            // read.  With one warp per frame the warp of the thread that straddles the row end is the whole frame:
+            // the register masks below cost it 33 x (2 ISETP + 2 FSEL) issue slots, 5 % of the kernel.
+            constexpr bool ZERO_TAIL = (NW == 1) && !CPLX;
+            if constexpr (ZERO_TAIL) {
+                for (int idx = n + tid; idx < TPF * E; idx += TPF) sts32(sb + LAND + cur_lead_u + 4u * idx, 0.0f);
+                for (int idx = m + tid; idx < TPF * E; idx += TPF) sts32(sb + LAND + LY::LAND_ROW + cur_lead_v + 4u * idx, 0.0f);
+                __syncwarp();
+            }
 #pragma unroll
-            for (int c = 0; c < E; ++c) {  // (past the row: finite garbage inside the landing rows)
+            for (int c = 0; c < E; ++c) {  // (past the row: zeros, or finite garbage inside the landing rows that is masked)
                 if constexpr (CPLX) {  // |z|^2 = re^2 + im^2 directly (no square root), or |z|
                     float re, im;
                     lds64(rawU + 8 * c, re, im);
@@ -758,10 +768,13 @@ __global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout
                     x2[c] = lds32x2(rawU + 4 * c, rawV + 4 * c);
                 }
             }
-            if (!inside) {
+            if constexpr (!ZERO_TAIL) {
+                if (!inside) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x2[c] = mask2(x2[c], e0 + c < n, e0 + c < m);
+                    for (int c = 0; c < E; ++c) x2[c] = mask2(x2[c], e0 + c < n, e0 + c < m);
+                }
             }
+            (void)inside;
             const bool sq = square && !CPLX;
             // Weights used as given (module-level `wasserstein_1d`, kernel mode MODE_RAW): the CDF is a plain
             // cumsum, which the reference accumulates in fp64 -- reproduced exactly, because with a handful of
