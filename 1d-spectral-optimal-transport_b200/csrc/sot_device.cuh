@@ -64,7 +64,8 @@ SOT_DEVINL void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.re
 // make generic-proxy shared-memory writes visible to the async (TMA) proxy
 SOT_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// |d|^p; PMODE 2 -> d*d compiled in (losses.py:313 with p=2); PMODE 0 -> any p at run time:
+// |d|^p; PMODE 2 -> d*d compiled in (losses.py:313 with p=2); PMODE 3 -> the same, in a kernel that also has NO cutoff
+// mask compiled into its merge walk (limit_quantile_range off: the BASELINE "NoCut" sweep); PMODE 0 -> any p at run time:
 // d*d for 2, |d| for 1 (:311-312), powf(|d|, p) otherwise (:313)
 template <int PMODE>
 SOT_DEVINL float cost_of_gap(float d, float p);
@@ -78,7 +79,7 @@ template <int PMODE>
 SOT_DEVINL float cost_of_gap(float d, float p) {
     // __fmul_rn: never contracted into an FMA with a later subtraction, so |d|^2 is rounded
     // once on its own exactly like the reference's `diff.pow(2)` tensor (losses.py:313)
-    if constexpr (PMODE == 2) {
+    if constexpr (PMODE == 2 || PMODE == 3) {
         return __fmul_rn(d, d);
     } else {
         if (p == 2.0f) return __fmul_rn(d, d);

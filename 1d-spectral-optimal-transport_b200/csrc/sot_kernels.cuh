@@ -557,6 +557,11 @@ __global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout
     sot_frame_kernel(const FrameArgs args) {
     static_assert(NCH == 1 || NCH == 2, "one or two merge chains per thread");
     constexpr bool SUB = FPW > 1;
+    // PMODE 3: p = 2 and no quantile cutoff -- the walk's per-slot mask (FFMA.SAT + FMUL, 2 of its 24 instructions per
+    // merged slot) is not compiled in; results are bit-identical to PMODE 2 run without FLAG_LIMIT (keep == 1 there)
+    constexpr bool NOLIM = (PMODE == 3);
+    static_assert(!NOLIM || (UNI && !CPLX && MODE == MODE_SPECTRA && OUT != OUT_PLAN),
+                  "no-cutoff walk: uniform grid, real spectra, loss / gradient outputs");
     static_assert(!SUB || (TPF * FPW == 32 && !CPLX && MODE == MODE_SPECTRA && OUT != OUT_PLAN),
                   "sub-warp frames: one warp per CTA, real spectra, loss / gradient outputs");
     static_assert(RS >= TPF * E + 8, "rows hold every thread's E entries (stored without guards) plus the lead / sentinel");
@@ -989,9 +994,12 @@ __global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout
                     constexpr int ch = decltype(CH)::value;
                     const float q = fminf(a[ch], b[ch]);
                     const float D = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
-                    float keep;
-                    asm("fma.rn.sat.f32 %0, %1, 0fDD800000, %2;" : "=f"(keep) : "f"(q), "f"(keep_c));  // q * -2^60 + c
-                    const float dq = __fmul_rn(q - qprev[ch], keep);
+                    float dq = q - qprev[ch];
+                    if constexpr (!NOLIM) {
+                        float keep;
+                        asm("fma.rn.sat.f32 %0, %1, 0fDD800000, %2;" : "=f"(keep) : "f"(q), "f"(keep_c));  // q * -2^60 + c
+                        dq = __fmul_rn(dq, keep);
+                    }
                     acc[ch] = fmaf(dq, D, acc[ch]);
                     qprev[ch] = q;
                     uint32_t consumed;
@@ -1057,9 +1065,12 @@ __global__ void __launch_bounds__(TPF * FPW, min_ctas(TPF * FPW, E, FPW * Layout
                     constexpr int ch = decltype(CH)::value;
                     const float q = fminf(a[ch], b[ch]);
                     const float D = UNI ? cost_of_gap<PMODE>(pa[ch], args.p) : transport_cost<PMODE>(pa[ch], pb[ch], args.p);
-                    float keep;  // 1 for q <= thr, 0 above (fma pipe, see keep_c)
-                    asm("fma.rn.sat.f32 %0, %1, 0fDD800000, %2;" : "=f"(keep) : "f"(q), "f"(keep_c));
-                    const float fmd = __fmul_rn(D, keep);  // m * d of a group that starts here
+                    float fmd = D;  // m * d of a group that starts here
+                    if constexpr (!NOLIM) {
+                        float keep;  // 1 for q <= thr, 0 above (fma pipe, see keep_c)
+                        asm("fma.rn.sat.f32 %0, %1, 0fDD800000, %2;" : "=f"(keep) : "f"(q), "f"(keep_c));
+                        fmd = __fmul_rn(D, keep);
+                    }
                     acc[ch] = fmaf(q - qprev[ch], fmd, acc[ch]);
                     const bool same = (q == qprev[ch]);
                     const float md = same ? md_prev[ch] : fmd;

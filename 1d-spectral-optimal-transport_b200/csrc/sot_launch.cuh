@@ -55,6 +55,9 @@ cudaError_t launch_subwarp(const LaunchRequest& r, cudaStream_t stream) {
     const bool uniform = (a.flags & FLAG_UNIFORM) && a.pos_u_stride == 0 && a.pos_v_stride == 0 && a.n >= 2;
     const bool p2 = (a.p == 2.0f);
     const bool grad = (r.out == OUT_GRAD);
+    if (uniform && p2 && !(a.flags & FLAG_LIMIT))  // no cutoff: the walk without its per-slot mask (PMODE 3)
+        return grad ? launch_one<TPF, E, RS, NCH, true, false, 3, OUT_GRAD, MODE_SPECTRA, FPW>(a, stream)
+                    : launch_one<TPF, E, RS, NCH, true, false, 3, OUT_LOSS, MODE_SPECTRA, FPW>(a, stream);
     if (uniform) {
         if (grad) return p2 ? launch_one<TPF, E, RS, NCH, true, false, 2, OUT_GRAD, MODE_SPECTRA, FPW>(a, stream)
                             : launch_one<TPF, E, RS, NCH, true, false, 0, OUT_GRAD, MODE_SPECTRA, FPW>(a, stream);
@@ -77,6 +80,11 @@ cudaError_t launch_modes(const LaunchRequest& r, cudaStream_t stream) {
                           : launch_one<TPF, E, RS, NCH, UNI, true, 0, OUT_LOSS, MODE_SPECTRA>(r.args, stream);
             return p2 ? launch_one<TPF, E, RS, NCH, UNI, true, 2, OUT_GRAD, MODE_SPECTRA>(r.args, stream)
                       : launch_one<TPF, E, RS, NCH, UNI, true, 0, OUT_GRAD, MODE_SPECTRA>(r.args, stream);
+        }
+        if constexpr (UNI) {
+            if (p2 && !(r.args.flags & FLAG_LIMIT))  // no cutoff: the walk without its per-slot mask (PMODE 3)
+                return r.out == OUT_LOSS ? launch_one<TPF, E, RS, NCH, true, false, 3, OUT_LOSS, MODE_SPECTRA>(r.args, stream)
+                                         : launch_one<TPF, E, RS, NCH, true, false, 3, OUT_GRAD, MODE_SPECTRA>(r.args, stream);
         }
         if (r.out == OUT_LOSS)
             return p2 ? launch_one<TPF, E, RS, NCH, UNI, false, 2, OUT_LOSS, MODE_SPECTRA>(r.args, stream)
