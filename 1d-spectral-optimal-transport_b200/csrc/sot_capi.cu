@@ -500,6 +500,20 @@ cudaError_t sync_positions(float** dev, size_t* cap, float** shadow, size_t* len
     return cudaMemcpyAsync(*dev, copy, 4 * n, cudaMemcpyHostToDevice, stream);
 }
 
+// Device address of a host buffer the GPU can reach directly (pinned by cudaHostAlloc / cudaHostRegister under unified
+// addressing), or nullptr: pageable memory, or a pointer the runtime does not know.
+template <typename T>
+T* mapped_device_pointer(T* host) {
+    if (host == nullptr) return nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+        cudaGetLastError();  // (older runtimes report unknown pointers as an error: clear it)
+        return nullptr;
+    }
+    if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) return nullptr;
+    return static_cast<T*>(const_cast<void*>(static_cast<const void*>(attr.devicePointer)));
+}
+
 void release(HostWorkspace& w) {
     for (int k = 0; k < kSlots; ++k) {
         HostSlot& s = w.slot[k];
@@ -565,6 +579,38 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
 
     HostWorkspace& w = g_ws[device];
     int rc = SOT_OK;
+    // Zero-copy (SOT_HOST_ZEROCOPY=1; shared supports; every buffer pinned and mapped): ONE launch over the whole batch
+    // whose bulk loads and stores go over PCIe themselves -- no staging buffers, no fill and drain of a copy pipeline.
+    // Anything else (pageable memory, per-frame supports) takes the chunked pipeline below.
+    if (const char* zc = getenv("SOT_HOST_ZEROCOPY"); zc != nullptr && zc[0] == '1' && su && sv) {
+        const float* du = mapped_device_pointer(hp->u);
+        const float* dv = mapped_device_pointer(hp->v);
+        const float* dup = mapped_device_pointer(upstream);
+        float* dl = mapped_device_pointer(loss);
+        float* dgu = mapped_device_pointer(grad_u);
+        float* dgv = mapped_device_pointer(grad_v);
+        const bool all_mapped = du != nullptr && dv != nullptr && (upstream == nullptr || dup != nullptr) &&
+                                (loss != nullptr && dl != nullptr) && (grad_u == nullptr || dgu != nullptr) &&
+                                (grad_v == nullptr || dgv != nullptr);
+        if (all_mapped) {
+            if (w.s_k == nullptr) {
+                e = cudaStreamCreateWithFlags(&w.s_k, cudaStreamNonBlocking);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithFlags");
+            }
+            e = sync_positions(&w.d_pu, &w.cap_dpu, &w.h_pu, &w.len_pu, hp->pos_u, n, w.s_k);
+            if (e == cudaSuccess) e = sync_positions(&w.d_pv, &w.cap_dpv, &w.h_pv, &w.len_pv, hp->pos_v, m, w.s_k);
+            if (e != cudaSuccess) return cuda_fail(e, "sync_positions");
+            sot_problem dp = *hp;
+            dp.u = du;
+            dp.v = dv;
+            dp.pos_u = w.d_pu;
+            dp.pos_v = w.d_pv;
+            rc = want_grad ? sot_forward_backward_device(&dp, dup, dl, dgu, dgv, w.s_k) : sot_forward_device(&dp, dl, w.s_k);
+            e = cudaStreamSynchronize(w.s_k);
+            if (rc == SOT_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+            return rc;
+        }
+    }
     constexpr int kTraceChunks = 64;
     const bool trace = getenv("SOT_HOST_TRACE") != nullptr;
     cudaEvent_t tev[4 * kTraceChunks] = {};
@@ -581,9 +627,9 @@ int sot_loss_grad_host(const sot_problem* hp, const float* upstream, float* loss
     } while (0)
     {
         if (!w.ready) {
-            SOT_CK(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
-            SOT_CK(cudaStreamCreateWithFlags(&w.s_k, cudaStreamNonBlocking));
-            SOT_CK(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+            if (w.s_in == nullptr) SOT_CK(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
+            if (w.s_k == nullptr) SOT_CK(cudaStreamCreateWithFlags(&w.s_k, cudaStreamNonBlocking));  // (zero-copy calls make it too)
+            if (w.s_out == nullptr) SOT_CK(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
             for (int k = 0; k < kSlots; ++k) {
                 SOT_CK(cudaEventCreateWithFlags(&w.slot[k].in_done, cudaEventDisableTiming));
                 SOT_CK(cudaEventCreateWithFlags(&w.slot[k].k_done, cudaEventDisableTiming));

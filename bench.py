@@ -535,7 +535,9 @@ def main():
         e2e = {"value": frames * world * n_e2e / t.item(), "unit": "frames/s",
                "h2d_bytes_per_step": 4 * frames * (2 * F + 1) + 8 * F,
                "d2h_bytes_per_step": 4 * frames * (2 * F + 1), "steps": n_e2e,
-               "api": "sot_loss_grad_host (C ABI, pinned host buffers, chunked 3-stream pipeline)",
+               "api": "sot_loss_grad_host (C ABI, pinned host buffers, " +
+                      ("zero-copy: one launch reads and writes host memory over PCIe)"
+                       if os.environ.get("SOT_HOST_ZEROCOPY", "")[:1] == "1" else "chunked 3-stream pipeline)"),
                "host_binding": bind}
 
     cb = None

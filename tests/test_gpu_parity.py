@@ -838,6 +838,28 @@ def test_host_buffer_entry_point_matches_device_path(capi):
     assert torch.equal(loss, d[0].cpu()) and torch.equal(gu, d[1].cpu()) and torch.equal(gv, d[2].cpu())
 
 
+@pytest.mark.parametrize("n_frames,n_bins", [(37, 1025), (300, 257), (5, 513)])
+def test_host_buffer_entry_point_zero_copy_matches_device_path(capi, monkeypatch, n_frames, n_bins):
+    """SOT_HOST_ZEROCOPY=1 with every buffer pinned: the kernels read the spectra from and write loss and gradients to
+    host memory themselves (one launch, no staging copies).  Same numbers as the device path, bit for bit; with a
+    pageable buffer among them the call falls back to the copy pipeline (same numbers again)."""
+    gen = torch.Generator().manual_seed(n_frames)
+    x = torch.rand(n_frames, n_bins, generator=gen).pin_memory()
+    y = torch.rand(n_frames, n_bins, generator=gen).pin_memory()
+    pos = torch.linspace(0, 1, n_bins)
+    flags = capi.SOT_SQUARE | capi.SOT_CUT_SCALE | capi.SOT_LIMIT
+    up = torch.rand(n_frames, generator=gen).pin_memory()
+    d = capi.forward_backward(x.to(DEV), y.to(DEV), pos.to(DEV), pos.to(DEV), 2.0, flags, upstream=up.to(DEV))
+    torch.cuda.synchronize()
+    monkeypatch.setenv("SOT_HOST_ZEROCOPY", "1")
+    for pinned_out in (True, False):
+        out = {"loss": torch.full((n_frames,), -1.0), "grad_u": torch.full_like(x, -1.0), "grad_v": torch.full_like(y, -1.0)}
+        if pinned_out:
+            out = {k: v.pin_memory() for k, v in out.items()}
+        loss, gu, gv = capi.loss_grad_host(x, y, pos, pos, 2.0, flags, upstream=up, out=out)
+        assert torch.equal(loss, d[0].cpu()) and torch.equal(gu, d[1].cpu()) and torch.equal(gv, d[2].cpu()), pinned_out
+
+
 @pytest.mark.parametrize("n_bins", [257, 1025, 2049])
 @pytest.mark.parametrize("cut", [False, True])
 def test_cdf_rows_are_monotone_on_heavy_tailed_spectra(capi, n_bins, cut):
