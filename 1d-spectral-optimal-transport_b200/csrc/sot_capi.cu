@@ -288,6 +288,10 @@ int sot_forward_backward_device(const sot_problem* prob, const float* upstream, 
     return launch(prob, r, stream);
 }
 
+// One co-rank per merge chunk.  The chunk boundaries depend on the row lengths and on the NUMBER of chunks only
+// (L = ceil((n_u + n_v) / chunks) | 1, chunk c starts at merged slot c * L), not on how many bins a thread holds: two
+// configurations with the same threads x chains cut the merged grid identically, so co-ranks saved by one are valid
+// for the other -- the count is the whole compatibility condition.
 int sot_coranks_per_frame(int32_t n_u, int32_t n_v) {
     const Config* c = pick_config(n_u, n_v);
     return c == nullptr ? 0 : c->tpf * c->nch;
