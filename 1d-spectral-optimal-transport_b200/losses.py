@@ -17,7 +17,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["Wasserstein1D", "wasserstein_1d", "quantile_function", "sot_frames", "sot_mean"]
+__all__ = ["Wasserstein1D", "wasserstein_1d", "quantile_function", "sot_frames", "sot_mean", "position_term_from_plan"]
 
 BACKWARD_MODES = ("recompute", "fused")       # per-frame values (`sot_frames`: hinge, `dims`, `wasserstein_1d`)
 MEAN_BACKWARD_MODES = ("onepass", "recompute")  # the plain mean over all frames (every paper config)
@@ -100,10 +100,7 @@ def _rows(t: torch.Tensor, name: str) -> torch.Tensor:
 def _support(pos: torch.Tensor, like: torch.Tensor, name: str) -> torch.Tensor:
     """1-D -> shared grid (the reference `expand`s it, losses.py:167-170; an expanded view is
     recognised and collapsed back); 2-D / 3-D -> per-frame rows."""
-    if pos.requires_grad:
-        raise NotImplementedError("sot_b200: gradients w.r.t. support positions are not implemented "
-                                  "(the reference never requests them: trainer.py:187-197)")
-    pos = pos.detach()
+    pos = pos.detach()  # (gradients w.r.t. the positions, when asked for, come from `_position_term`)
     if pos.device != like.device:
         raise ValueError(f"sot_b200: `{name}` is on {pos.device} but the spectra are on {like.device}")
     if pos.dtype != torch.float32:
@@ -227,13 +224,79 @@ def _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_
     return u, v, pu, pv, flags
 
 
+# --------------------------------------------------------------------------------------
+# gradients w.r.t. the support positions
+# --------------------------------------------------------------------------------------
+def _wants_position_grad(x_pos, y_pos) -> bool:
+    return torch.is_grad_enabled() and (x_pos.requires_grad or y_pos.requires_grad)
+
+
+def position_term_from_plan(qs, iu, iv, pu, pv, p, limit) -> torch.Tensor:
+    """Per-frame loss (N,) as a function of the SORTED support positions `pu`, `pv` (1-D shared rows or (N, F)), the
+    transport plan held fixed: `qs` (N, K) merged quantile grid, `iu` / `iv` (N, K) un-clamped `searchsorted` indices.
+    This is losses.py:301-313 with `quantile_function`'s `xs[idx]` (losses.py:219-220) as the only place the positions
+    enter -- which is also the only way they enter the reference's autograd graph, so the gradients w.r.t. the
+    positions are the reference's.  Plain torch ops (runs wherever the tensors live; the CPU tests use it as is)."""
+    def take(pos, idx):
+        idx = idx.long().clamp(max=pos.shape[-1] - 1)  # losses.py:220
+        return pos[idx] if pos.ndim == 1 else torch.gather(pos, 1, idx)
+    delta = qs - torch.nn.functional.pad(qs, pad=(1, 0))[..., :-1]  # losses.py:301-304
+    if limit:
+        delta = torch.where(qs > 1, torch.zeros_like(delta), delta)  # losses.py:306-307
+    diff = torch.abs(take(pu, iu) - take(pv, iv))
+    return torch.sum(delta * (diff if p == 1 else diff.pow(p)), 1)  # losses.py:311-313
+
+
+def _position_term(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights) -> torch.Tensor:
+    """Per-frame loss attached to the autograd graph of x_pos / y_pos only (the spectra are constants here): the plan
+    kernel (`OUT_PLAN`) finds the merged grid and the indices, `position_term_from_plan` is differentiated by torch.
+    A path the paper's configurations never take (trainer.py:187-197 builds the positions without gradients): an extra
+    plan launch and ATen-sized temporaries, only when a position tensor requires a gradient."""
+    x, y = x.detach(), y.detach()
+    x, y = (x.abs() if x.is_complex() else x), (y.abs() if y.is_complex() else y)
+    u, v = _rows(x, "x"), _rows(y, "y")
+
+    def attached(pos, like):  # `_support` without the detach
+        pos = pos.to(torch.float32)
+        if pos.ndim == 3:
+            pos = pos.reshape(-1, pos.shape[-1])
+        if pos.ndim == 2 and (pos.shape[0] == 1 or pos.stride(0) == 0):
+            pos = pos[0]
+        _support(pos, like, "positions")  # shape / device checks
+        return pos
+
+    pu, pv = attached(x_pos, u), attached(y_pos, v)
+    sort_u, sort_v = require_sort if isinstance(require_sort, tuple) else (require_sort, require_sort)
+
+    def ordered(pos, w):  # `_order` with the sorted positions kept in the graph
+        if pos.ndim == 1:
+            pos_sorted, perm = torch.sort(pos, stable=True)
+            return pos_sorted, w.index_select(1, perm)
+        pos_sorted, perm = torch.sort(pos, dim=1, stable=True)
+        return pos_sorted, torch.gather(w, 1, perm)
+
+    if sort_u:
+        pu, u = ordered(pu, u)
+    if sort_v:
+        pv, v = ordered(pv, v)
+    flags = ((_capi.SOT_SQUARE if square else 0) | (_capi.SOT_CUT_SCALE if cut_scale else 0) |
+             (_capi.SOT_RAW_WEIGHTS if raw_weights else 0))
+    _, _, qs, _, _, iu, iv = _capi.quantiles(u.contiguous(), v.contiguous(), pu.detach().contiguous(),
+                                             pv.detach().contiguous(), flags, want_indices=True)
+    return position_term_from_plan(qs, iu, iv, pu, pv, p, limit)
+
+
 def sot_frames(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=False, require_sort=True,
                raw_weights=False, backward_mode="recompute") -> torch.Tensor:
-    """Per-frame W_p^p, shape (N,), differentiable w.r.t. x and y."""
+    """Per-frame W_p^p, shape (N,), differentiable w.r.t. x and y (and, through `_position_term`, the positions)."""
     if backward_mode not in BACKWARD_MODES:
         raise ValueError(f"backward_mode must be one of {BACKWARD_MODES}")
     u, v, pu, pv, flags = _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights)
-    return _SotFrames.apply(u, v, pu, pv, float(p), flags, backward_mode)
+    rows = _SotFrames.apply(u, v, pu, pv, float(p), flags, backward_mode)
+    if _wants_position_grad(x_pos, y_pos):  # value unchanged (+ exactly 0); the gradient w.r.t. the positions rides on it
+        term = _position_term(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights)
+        rows = rows + (term - term.detach())
+    return rows
 
 
 class _SotMean(torch.autograd.Function):
@@ -293,7 +356,14 @@ def sot_mean(x, y, x_pos, y_pos, p=1, square=False, cut_scale=False, limit=False
     if backward_mode not in MEAN_BACKWARD_MODES:
         raise ValueError(f"backward_mode must be one of {MEAN_BACKWARD_MODES}")
     u, v, pu, pv, flags = _prepare(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights)
-    return _SotMean.apply(u, v, pu, pv, float(p), flags, exchange, backward_mode)
+    value = _SotMean.apply(u, v, pu, pv, float(p), flags, exchange, backward_mode)
+    if _wants_position_grad(x_pos, y_pos):
+        if exchange is not None:
+            raise NotImplementedError("sot_b200: gradients w.r.t. support positions are not available for the sharded "
+                                      "mean (use the plain Wasserstein1D and reduce the position gradients yourself)")
+        term = _position_term(x, y, x_pos, y_pos, p, square, cut_scale, limit, require_sort, raw_weights).mean()
+        value = value + (term - term.detach())
+    return value
 
 
 # --------------------------------------------------------------------------------------
